@@ -1,0 +1,84 @@
+"""Builds the in-tree C-ABI shared library `boxdreamer_b200/libboxdreamer_b200.so` for sm_100a.
+
+    python -m boxdreamer_b200.build [--force] [--verbose]
+
+nvcc cross-compiles without a GPU; the built .so travels with the repo snapshot to the GPU box
+(it is git-ignored, not gpurun-ignored).  cudart is linked statically and the driver API is only
+reached through cudaGetDriverEntryPoint, so the library loads (and exports its symbols) on a
+CPU-only host too.
+"""
+from __future__ import annotations
+
+import argparse
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libboxdreamer_b200.so")
+SOURCES = ["gemm_tc.cu", "attn_tc.cu", "kernels_simt.cu", "post.cu", "bd_engine.cu"]
+HEADERS = ["common.cuh", "bd_internal.h", os.path.join("..", "..", "include", "boxdreamer_b200.h")]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found")
+    return exe
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(BUILD, exist_ok=True)
+    nvcc = _nvcc()
+    hdrs = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
+    flags = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + ARCH
+    if verbose:
+        flags += ["-Xptxas", "-v"]
+    jobs = []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(BUILD, src.replace(".cu", ".o"))
+        if force or _stale(o, [s] + hdrs):
+            jobs.append((s, o))
+
+    def compile_one(job):
+        s, o = job
+        cmd = [nvcc] + flags + ["-c", s, "-o", o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return job, r
+
+    if jobs:
+        with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            for (s, o), r in ex.map(compile_one, jobs):
+                if verbose or r.returncode != 0:
+                    sys.stderr.write(f"--- {os.path.basename(s)}\n{r.stdout}{r.stderr}\n")
+                if r.returncode != 0:
+                    raise RuntimeError(f"nvcc failed on {s}")
+    objs = [os.path.join(BUILD, src.replace(".cu", ".o")) for src in SOURCES]
+    if force or jobs or _stale(LIB, objs):
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ARCH + ["-cudart", "static", "-Xcompiler", "-fPIC"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    print(build(a.force, a.verbose))

@@ -1,0 +1,573 @@
+// C ABI + native engine: owns the workspace and packed weights, enqueues the whole BoxDreamer
+// inference path (DINOv2 ViT-B/14-reg -> BETR decoder -> heat maps -> top-20 corners -> PnP) on one stream.
+// See include/boxdreamer_b200.h for the contract and the reference call sites each entry replaces.
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/boxdreamer_b200.h"
+#include "bd_internal.h"
+
+using namespace bd;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(expr)                                                                                           \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess) {                                                                               \
+      std::string _m = std::string(#expr) + ": " + cudaGetErrorString(_e);                                 \
+      const char* _t = tc_last_error();                                                                    \
+      if (_t && _t[0]) _m += std::string(" [") + _t + "]";                                                 \
+      return fail(BD_ERR_CUDA, _m);                                                                        \
+    }                                                                                                      \
+  } while (0)
+
+struct Weight {
+  float* f32 = nullptr;   // device, fp32
+  bf16* b16 = nullptr;    // device, bf16 (tensor path, GEMM operands only)
+  std::vector<int64_t> shape;
+  size_t numel = 0;
+};
+
+struct bd_engine {
+  bd_config cfg;
+  int device = 0;
+  bool tc = false;
+  bool finalized = false;
+  int S, patch, g, P, d, hd_dec, hd_dino, n_tok, n_prefix, seqpad_dino, kpe;  // kpe: patch-embed K (padded on the tensor path)
+  int Lmax, Bmax, Tmax;
+  std::map<std::string, Weight> w;
+  std::vector<void*> allocs;
+  // workspace (element type depends on precision: "act" = bf16 on the tensor path, fp32 on the exact path)
+  void* A_pe = nullptr;      // act [L*P, kpe]
+  float* X_dino = nullptr;   // f32 [L*n_tok, d]
+  float* X_dec = nullptr;    // f32 [L*P, d]
+  void* H = nullptr;         // act [Mmax, d]      LayerNorm output
+  void* G = nullptr;         // act [Mmax, 4d]     MLP hidden
+  void* Q = nullptr; void* K = nullptr; void* V = nullptr;  // act, attention operand layouts
+  void* O = nullptr;         // act [Mmax, d]
+  float* qkv_scratch = nullptr;  // exact path: f32 [Mmax, 3d]
+  float* feats = nullptr;    // f32 [L*P, d]
+  void* feats_act = nullptr; // act [L*P, d]
+  float* R = nullptr;        // f32 [L*P, d]
+  float* PF = nullptr;       // f32 [L*P, d]
+  void* A_bb = nullptr;      // act [L*P, patch*patch*8]
+  void* Xq = nullptr;        // act [B*P, d]
+  float* logits = nullptr;   // f32 [B*P, patch*patch*8]
+  float* heat = nullptr;     // f32 [B,8,S,S]
+  float* corners_px = nullptr; float* corners_norm = nullptr; float* poses = nullptr;
+  float* bbox3d_q = nullptr; float* K_q = nullptr; int64_t* qidx = nullptr;
+  void* in_images = nullptr; void* in_bbox = nullptr;  // device staging for bd_forward_host
+  float* pos_dec = nullptr;  // f32 [P, d] 2-D sincos table
+  cudaStream_t host_stream = nullptr;
+};
+
+static size_t act_size(const bd_engine* e) { return e->tc ? 2 : 4; }
+
+static int dalloc(bd_engine* e, void** out, size_t bytes) {
+  void* p = nullptr;
+  CK(cudaMalloc(&p, bytes ? bytes : 16));
+  CK(cudaMemset(p, 0, bytes ? bytes : 16));
+  e->allocs.push_back(p);
+  *out = p;
+  return BD_OK;
+}
+#define DALLOC(field, bytes)                                               \
+  do {                                                                     \
+    int _r = dalloc(e, reinterpret_cast<void**>(&(field)), (bytes));       \
+    if (_r != BD_OK) return _r;                                            \
+  } while (0)
+
+extern "C" const char* bd_last_error(void) { return g_err.c_str(); }
+extern "C" int bd_version(void) { return 100; }
+
+// pos_encodiong.py:125-213 as consumed at betr.py:357-364 (see oracle sincos_pos_embed_2d)
+static void build_sincos(std::vector<float>& tab, int d, int g) {
+  const int half = d / 2, quarter = d / 4;
+  tab.assign(static_cast<size_t>(g) * g * d, 0.f);
+  for (int y = 0; y < g; ++y)
+    for (int x = 0; x < g; ++x) {
+      float* row = &tab[(static_cast<size_t>(y) * g + x) * d];
+      for (int i = 0; i < quarter; ++i) {
+        const double omega = 1.0 / pow(10000.0, static_cast<double>(i) / (half / 2.0));
+        const double ax = static_cast<double>(static_cast<float>(x)) * omega;
+        const double ay = static_cast<double>(static_cast<float>(y)) * omega;
+        row[i] = static_cast<float>(sin(ax));
+        row[quarter + i] = static_cast<float>(cos(ax));
+        row[half + i] = static_cast<float>(sin(ay));
+        row[half + quarter + i] = static_cast<float>(cos(ay));
+      }
+    }
+}
+
+extern "C" int bd_create(bd_handle* out, const bd_config* cfg) {
+  if (!out || !cfg) return fail(BD_ERR_INVALID, "bd_create: null argument");
+  if (cfg->patch_size <= 0 || cfg->img_size % cfg->patch_size != 0)
+    return fail(BD_ERR_INVALID, "bd_create: img_size must be a multiple of patch_size");
+  if (cfg->d_model != 768 || cfg->dec_heads != 8 || cfg->dino_heads != 12)
+    return fail(BD_ERR_UNSUPPORTED, "bd_create: only d_model=768, decoder 8x96, DINOv2 12x64 are built");
+  if (cfg->max_batch <= 0 || cfg->max_views <= 0) return fail(BD_ERR_INVALID, "bd_create: max_batch/max_views must be > 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(BD_ERR_CUDA, "bd_create: no CUDA device (this library has no CPU fallback)");
+  bd_engine* e = new bd_engine();
+  e->cfg = *cfg;
+  CK(cudaGetDevice(&e->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, e->device));
+  e->tc = cfg->precision == BD_PRECISION_BF16;
+  if (e->tc && prop.major != 10) {
+    delete e;
+    return fail(BD_ERR_UNSUPPORTED, "bd_create: the bf16 tensor path needs an sm_100 (Blackwell) device");
+  }
+  tc_set_num_sms(prop.multiProcessorCount);
+  e->S = cfg->img_size; e->patch = cfg->patch_size; e->g = e->S / e->patch; e->P = e->g * e->g; e->d = cfg->d_model;
+  e->hd_dec = e->d / cfg->dec_heads; e->hd_dino = e->d / cfg->dino_heads;
+  e->n_prefix = 1 + cfg->dino_registers; e->n_tok = e->n_prefix + e->P;
+  e->seqpad_dino = (e->n_tok + 127) / 128 * 128;
+  const int kreal = 3 * e->patch * e->patch;
+  e->kpe = e->tc ? (kreal + 63) / 64 * 64 : kreal;
+  e->Bmax = cfg->max_batch; e->Tmax = cfg->max_views; e->Lmax = e->Bmax * e->Tmax;
+  const size_t as = act_size(e);
+  const size_t L = e->Lmax, P = e->P, d = e->d;
+  const size_t Md = L * e->n_tok, Mb = L * P, Mmax = Md > Mb ? Md : Mb;
+  const size_t seqpad_dec = (static_cast<size_t>(e->Tmax) * P + 127) / 128 * 128;
+  const size_t qk_dino = L * cfg->dino_heads * e->seqpad_dino * e->hd_dino;
+  const size_t qk_dec = static_cast<size_t>(e->Bmax) * cfg->dec_heads * seqpad_dec * e->hd_dec;
+  const size_t qk = qk_dino > qk_dec ? qk_dino : qk_dec;
+  const size_t pp8 = static_cast<size_t>(e->patch) * e->patch * 8;
+  DALLOC(e->A_pe, Mb * e->kpe * as);
+  DALLOC(e->X_dino, Md * d * 4);
+  DALLOC(e->X_dec, Mb * d * 4);
+  DALLOC(e->H, Mmax * d * as);
+  DALLOC(e->G, Mmax * 4 * d * as);
+  DALLOC(e->Q, qk * as);
+  DALLOC(e->K, qk * as);
+  DALLOC(e->V, qk * as);
+  DALLOC(e->O, Mmax * d * as);
+  if (!e->tc) DALLOC(e->qkv_scratch, Mmax * 3 * d * 4);
+  DALLOC(e->feats, Mb * d * 4);
+  DALLOC(e->feats_act, Mb * d * as);
+  DALLOC(e->R, Mb * d * 4);
+  DALLOC(e->PF, Mb * d * 4);
+  DALLOC(e->A_bb, Mb * pp8 * as);
+  DALLOC(e->Xq, static_cast<size_t>(e->Bmax) * P * d * as);
+  DALLOC(e->logits, static_cast<size_t>(e->Bmax) * P * pp8 * 4);
+  DALLOC(e->heat, static_cast<size_t>(e->Bmax) * 8 * e->S * e->S * 4);
+  DALLOC(e->corners_px, static_cast<size_t>(e->Bmax) * 16 * 4);
+  DALLOC(e->corners_norm, static_cast<size_t>(e->Bmax) * 16 * 4);
+  DALLOC(e->poses, static_cast<size_t>(e->Bmax) * 16 * 4);
+  DALLOC(e->bbox3d_q, static_cast<size_t>(e->Bmax) * 24 * 4);
+  DALLOC(e->K_q, static_cast<size_t>(e->Bmax) * 9 * 4);
+  DALLOC(e->qidx, static_cast<size_t>(e->Bmax) * 8);
+  DALLOC(e->pos_dec, P * d * 4);
+  std::vector<float> tab;
+  build_sincos(tab, e->d, e->g);
+  CK(cudaMemcpy(e->pos_dec, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+  *out = e;
+  return BD_OK;
+}
+
+extern "C" int bd_destroy(bd_handle e) {
+  if (!e) return BD_OK;
+  cudaDeviceSynchronize();
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->host_stream) cudaStreamDestroy(e->host_stream);
+  delete e;
+  return BD_OK;
+}
+
+extern "C" int bd_load_weight(bd_handle e, const char* name, const void* data, const int64_t* shape, int32_t ndim) {
+  if (!e || !name || !data || (ndim > 0 && !shape)) return fail(BD_ERR_INVALID, "bd_load_weight: null argument");
+  size_t n = 1;
+  std::vector<int64_t> shp;
+  for (int i = 0; i < ndim; ++i) { n *= static_cast<size_t>(shape[i]); shp.push_back(shape[i]); }
+  Weight& w = e->w[name];
+  if (w.f32 == nullptr || w.numel != n) {
+    void* p = nullptr;
+    int r = dalloc(e, &p, n * 4);
+    if (r != BD_OK) return r;
+    w.f32 = reinterpret_cast<float*>(p);
+    w.numel = n;
+    w.b16 = nullptr;
+  }
+  w.shape = shp;
+  CK(cudaMemcpy(w.f32, data, n * 4, cudaMemcpyDefault));
+  e->finalized = false;
+  return BD_OK;
+}
+
+static int expect(bd_engine* e, const std::string& name, std::vector<int64_t> shape) {
+  auto it = e->w.find(name);
+  if (it == e->w.end()) return fail(BD_ERR_STATE, "missing weight: " + name);
+  size_t n = 1;
+  for (auto s : shape) n *= static_cast<size_t>(s);
+  if (it->second.numel != n) return fail(BD_ERR_STATE, "weight has the wrong size: " + name);
+  return BD_OK;
+}
+
+static int pack_bf16(bd_engine* e, const std::string& name) {
+  Weight& w = e->w[name];
+  if (!w.b16) {
+    void* p = nullptr;
+    int r = dalloc(e, &p, w.numel * 2);
+    if (r != BD_OK) return r;
+    w.b16 = reinterpret_cast<bf16*>(p);
+  }
+  CK(cast_f32_to_bf16(w.f32, w.b16, w.numel, 0));
+  return BD_OK;
+}
+
+extern "C" int bd_finalize_weights(bd_handle e) {
+  if (!e) return fail(BD_ERR_INVALID, "bd_finalize_weights: null handle");
+  const int64_t d = e->d, pp8 = static_cast<int64_t>(e->patch) * e->patch * 8;
+  std::vector<std::string> gemm_w;
+  int r;
+#define EXPECT(name, ...)                                   \
+  do {                                                      \
+    r = expect(e, (name), std::vector<int64_t>{__VA_ARGS__}); \
+    if (r != BD_OK) return r;                               \
+  } while (0)
+  EXPECT("decoder.bbox_learnable_query", 1, d);
+  for (int i = 0; i < e->cfg.dec_layers; ++i) {
+    const std::string p = "decoder.attn." + std::to_string(i) + ".";
+    EXPECT(p + "norm1.weight", d); EXPECT(p + "norm1.bias", d);
+    EXPECT(p + "attn.qkv.weight", 3 * d, d); EXPECT(p + "attn.qkv.bias", 3 * d);
+    EXPECT(p + "attn.q_norm.weight", e->hd_dec); EXPECT(p + "attn.k_norm.weight", e->hd_dec);
+    EXPECT(p + "attn.proj.weight", d, d); EXPECT(p + "attn.proj.bias", d);
+    EXPECT(p + "norm2.weight", d); EXPECT(p + "norm2.bias", d);
+    EXPECT(p + "mlp.fc1.weight", 4 * d, d); EXPECT(p + "mlp.fc1.bias", 4 * d);
+    EXPECT(p + "mlp.fc2.weight", d, 4 * d); EXPECT(p + "mlp.fc2.bias", d);
+    gemm_w.push_back(p + "attn.qkv.weight"); gemm_w.push_back(p + "attn.proj.weight");
+    gemm_w.push_back(p + "mlp.fc1.weight"); gemm_w.push_back(p + "mlp.fc2.weight");
+  }
+  EXPECT("decoder.bbox_proj.weight", pp8, d); EXPECT("decoder.bbox_proj.bias", pp8);
+  EXPECT("decoder.input_transform.fc1.weight", d, d); EXPECT("decoder.input_transform.fc1.bias", d);
+  EXPECT("decoder.input_transform.fc2.weight", d, d); EXPECT("decoder.input_transform.fc2.bias", d);
+  EXPECT("decoder.bbox_emb.weight", d, pp8); EXPECT("decoder.bbox_emb.bias", d);
+  gemm_w.push_back("decoder.bbox_proj.weight"); gemm_w.push_back("decoder.input_transform.fc1.weight");
+  gemm_w.push_back("decoder.input_transform.fc2.weight"); gemm_w.push_back("decoder.bbox_emb.weight");
+  EXPECT("dino.cls_token", 1, 1, d);
+  EXPECT("dino.pos_embed", 1, 1 + e->P, d);
+  EXPECT("dino.register_tokens", 1, e->cfg.dino_registers, d);
+  EXPECT("dino.patch_embed.proj.weight", d, 3, e->patch, e->patch);
+  EXPECT("dino.patch_embed.proj.bias", d);
+  for (int i = 0; i < e->cfg.dino_layers; ++i) {
+    const std::string p = "dino.blocks." + std::to_string(i) + ".";
+    EXPECT(p + "norm1.weight", d); EXPECT(p + "norm1.bias", d);
+    EXPECT(p + "attn.qkv.weight", 3 * d, d); EXPECT(p + "attn.qkv.bias", 3 * d);
+    EXPECT(p + "attn.proj.weight", d, d); EXPECT(p + "attn.proj.bias", d);
+    EXPECT(p + "ls1.gamma", d);
+    EXPECT(p + "norm2.weight", d); EXPECT(p + "norm2.bias", d);
+    EXPECT(p + "mlp.fc1.weight", 4 * d, d); EXPECT(p + "mlp.fc1.bias", 4 * d);
+    EXPECT(p + "mlp.fc2.weight", d, 4 * d); EXPECT(p + "mlp.fc2.bias", d);
+    EXPECT(p + "ls2.gamma", d);
+    gemm_w.push_back(p + "attn.qkv.weight"); gemm_w.push_back(p + "attn.proj.weight");
+    gemm_w.push_back(p + "mlp.fc1.weight"); gemm_w.push_back(p + "mlp.fc2.weight");
+  }
+  EXPECT("dino.norm.weight", d); EXPECT("dino.norm.bias", d);
+#undef EXPECT
+  if (e->tc) {
+    for (const auto& n : gemm_w) {
+      r = pack_bf16(e, n);
+      if (r != BD_OK) return r;
+    }
+    // patch-embed weight [d, 588] -> bf16 [d, kpe] zero padded (K multiple of 64 for the 128B-swizzle TMA boxes)
+    Weight& pw = e->w["dino.patch_embed.proj.weight"];
+    const int kreal = 3 * e->patch * e->patch;
+    std::vector<float> host(pw.numel);
+    CK(cudaMemcpy(host.data(), pw.f32, pw.numel * 4, cudaMemcpyDeviceToHost));
+    std::vector<float> padded(static_cast<size_t>(d) * e->kpe, 0.f);
+    for (int64_t o = 0; o < d; ++o)
+      for (int k = 0; k < kreal; ++k) padded[o * e->kpe + k] = host[o * kreal + k];
+    float* tmp = nullptr;
+    CK(cudaMalloc(&tmp, padded.size() * 4));
+    CK(cudaMemcpy(tmp, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice));
+    if (!pw.b16) {
+      void* p = nullptr;
+      r = dalloc(e, &p, padded.size() * 2);
+      if (r != BD_OK) { cudaFree(tmp); return r; }
+      pw.b16 = reinterpret_cast<bf16*>(p);
+    }
+    cudaError_t ce = cast_f32_to_bf16(tmp, pw.b16, padded.size(), 0);
+    cudaDeviceSynchronize();
+    cudaFree(tmp);
+    CK(ce);
+  }
+  CK(cudaDeviceSynchronize());
+  e->finalized = true;
+  return BD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+
+static const float* WF(bd_engine* e, const std::string& n) { return e->w[n].f32; }
+
+static cudaError_t linear(bd_engine* e, const void* in, const std::string& wname, int M, int N, int K, int epi, GemmEpi& ep,
+                          cudaStream_t s) {
+  Weight& w = e->w[wname];
+  if (e->tc) return gemm_tc(reinterpret_cast<const bf16*>(in), w.b16, M, N, K, epi, ep, s);
+  if (epi == EPI_QKV) ep.out_act = e->qkv_scratch;
+  return gemm_f32(reinterpret_cast<const float*>(in), w.f32, M, N, K, epi, ep, s);
+}
+
+static cudaError_t attention(bd_engine* e, int L, int heads, int hd, int seq, int seq_pad, cudaStream_t s) {
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  if (e->tc)
+    return attention_tc(reinterpret_cast<const bf16*>(e->Q), reinterpret_cast<const bf16*>(e->K), reinterpret_cast<const bf16*>(e->V),
+                        reinterpret_cast<bf16*>(e->O), L, heads, hd, seq, seq_pad, scale, e->cfg.attn_variant, s);
+  return attention_f32(reinterpret_cast<const float*>(e->Q), reinterpret_cast<const float*>(e->K),
+                       reinterpret_cast<const float*>(e->V), reinterpret_cast<float*>(e->O), L, heads, hd, seq, seq_pad, scale, s);
+}
+
+static cudaError_t ln_act(bd_engine* e, const float* x, const float* w, const float* b, float eps, int rows, cudaStream_t s) {
+  return layernorm(x, w, b, eps, e->tc ? nullptr : reinterpret_cast<float*>(e->H), e->tc ? reinterpret_cast<bf16*>(e->H) : nullptr,
+                   rows, e->d, 0, 0, 0, s);
+}
+
+// one pre-LN transformer block on the fp32 residual stream X [L*seq, d]
+static int run_block(bd_engine* e, float* X, const std::string& p, int L, int seq, int seq_pad, int heads, int hd, float ln_eps,
+                     bool qk_norm, const char* g1, const char* g2, cudaStream_t s) {
+  const int M = L * seq, d = e->d;
+  CK(ln_act(e, X, WF(e, p + "norm1.weight"), WF(e, p + "norm1.bias"), ln_eps, M, s));
+  GemmEpi q;
+  q.bias = WF(e, p + "attn.qkv.bias");
+  q.q = e->Q; q.k = e->K; q.v = e->V;
+  q.q_norm_w = qk_norm ? WF(e, p + "attn.q_norm.weight") : nullptr;
+  q.k_norm_w = qk_norm ? WF(e, p + "attn.k_norm.weight") : nullptr;
+  q.seq = seq; q.seq_pad = seq_pad; q.heads = heads; q.head_dim = hd; q.rms_eps = 1e-6f;
+  CK(linear(e, e->H, p + "attn.qkv.weight", M, 3 * d, d, EPI_QKV, q, s));
+  CK(attention(e, L, heads, hd, seq, seq_pad, s));
+  GemmEpi pr;
+  pr.bias = WF(e, p + "attn.proj.bias"); pr.out_f32 = X; pr.ldo = d; pr.gamma = g1 ? WF(e, p + g1) : nullptr;
+  CK(linear(e, e->O, p + "attn.proj.weight", M, d, d, EPI_RESID, pr, s));
+  CK(ln_act(e, X, WF(e, p + "norm2.weight"), WF(e, p + "norm2.bias"), ln_eps, M, s));
+  GemmEpi f1;
+  f1.bias = WF(e, p + "mlp.fc1.bias"); f1.out_act = e->G;
+  CK(linear(e, e->H, p + "mlp.fc1.weight", M, 4 * d, d, EPI_GELU, f1, s));
+  GemmEpi f2;
+  f2.bias = WF(e, p + "mlp.fc2.bias"); f2.out_f32 = X; f2.ldo = d; f2.gamma = g2 ? WF(e, p + g2) : nullptr;
+  CK(linear(e, e->G, p + "mlp.fc2.weight", M, d, 4 * d, EPI_RESID, f2, s));
+  return BD_OK;
+}
+
+static int dino_forward_impl(bd_engine* e, const void* images, int dtype, float* feats_out, int L, cudaStream_t s) {
+  if (!e->finalized) return fail(BD_ERR_STATE, "weights not finalised (call bd_finalize_weights)");
+  if (L <= 0 || L > e->Lmax) return fail(BD_ERR_INVALID, "bd_dino_forward: L exceeds max_batch*max_views");
+  const int P = e->P, d = e->d;
+  CK(im2col_patches(images, dtype == BD_BF16, e->A_pe, e->tc, L, e->S, e->patch, e->kpe, s));
+  GemmEpi pe;
+  pe.bias = WF(e, "dino.patch_embed.proj.bias");
+  pe.out_f32 = e->X_dino; pe.ldo = d;
+  pe.rp_in = P; pe.rp_out = e->n_tok; pe.rp_off = e->n_prefix;
+  pe.addtab = WF(e, "dino.pos_embed") + d;  // rows 1.. of the (already interpolated) table
+  CK(linear(e, e->A_pe, "dino.patch_embed.proj.weight", L * P, d, e->kpe, EPI_F32, pe, s));
+  CK(dino_prefix_tokens(e->X_dino, WF(e, "dino.cls_token"), WF(e, "dino.pos_embed"), WF(e, "dino.register_tokens"), L, e->n_tok,
+                        e->cfg.dino_registers, d, s));
+  for (int i = 0; i < e->cfg.dino_layers; ++i) {
+    int r = run_block(e, e->X_dino, "dino.blocks." + std::to_string(i) + ".", L, e->n_tok, e->seqpad_dino, e->cfg.dino_heads,
+                      e->hd_dino, 1e-6f, false, "ls1.gamma", "ls2.gamma", s);
+    if (r != BD_OK) return r;
+  }
+  // final LayerNorm, patch tokens only (vision_transformer.py:263-267)
+  CK(layernorm(e->X_dino, WF(e, "dino.norm.weight"), WF(e, "dino.norm.bias"), 1e-6f, feats_out,
+               e->tc ? reinterpret_cast<bf16*>(e->feats_act) : nullptr, L * P, d, P, e->n_tok, e->n_prefix, s));
+  return BD_OK;
+}
+
+static int decoder_forward_impl(bd_engine* e, const void* bbox_feat, int dtype, const float* feats, bool feats_act_valid,
+                                const int64_t* query_idx, float* heat_out, float* logits_out, int B, int T, cudaStream_t s) {
+  if (!e->finalized) return fail(BD_ERR_STATE, "weights not finalised (call bd_finalize_weights)");
+  if (B <= 0 || T <= 0 || B > e->Bmax || T > e->Tmax) return fail(BD_ERR_INVALID, "bd_decoder_forward: B/T exceed the workspace");
+  const int P = e->P, d = e->d, L = B * T, M = L * P;
+  const int pp8 = e->patch * e->patch * 8;
+  const void* fin = feats;
+  if (e->tc) {
+    if (!feats_act_valid) CK(cast_f32_to_bf16(feats, reinterpret_cast<bf16*>(e->feats_act), static_cast<size_t>(M) * d, s));
+    fin = e->feats_act;
+  }
+  // rgb branch: input_transform Mlp -> (LayerNorm without affine happens inside the fusion kernel)
+  GemmEpi t1;
+  t1.bias = WF(e, "decoder.input_transform.fc1.bias"); t1.out_act = e->G;
+  CK(linear(e, fin, "decoder.input_transform.fc1.weight", M, d, d, EPI_GELU, t1, s));
+  GemmEpi t2;
+  t2.bias = WF(e, "decoder.input_transform.fc2.bias"); t2.out_f32 = e->R; t2.ldo = d;
+  CK(linear(e, e->G, "decoder.input_transform.fc2.weight", M, d, d, EPI_F32, t2, s));
+  // pose branch: patchify(bbox_feat) -> bbox_emb
+  CK(patchify_heat(bbox_feat, dtype == BD_BF16, e->A_bb, e->tc, L, 8, e->S, e->patch, s));
+  GemmEpi be;
+  be.bias = WF(e, "decoder.bbox_emb.bias"); be.out_f32 = e->PF; be.ldo = d;
+  CK(linear(e, e->A_bb, "decoder.bbox_emb.weight", M, d, pp8, EPI_F32, be, s));
+  CK(betr_fuse(e->PF, e->R, WF(e, "decoder.bbox_learnable_query"), e->pos_dec, query_idx, e->X_dec, B, T, P, d, 1e-6f, s));
+  const int seq = T * P, seq_pad = (seq + 127) / 128 * 128;
+  for (int i = 0; i < e->cfg.dec_layers; ++i) {
+    int r = run_block(e, e->X_dec, "decoder.attn." + std::to_string(i) + ".", B, seq, seq_pad, e->cfg.dec_heads, e->hd_dec, 1e-5f,
+                      true, nullptr, nullptr, s);
+    if (r != BD_OK) return r;
+  }
+  CK(gather_query(e->X_dec, query_idx, e->tc ? nullptr : reinterpret_cast<float*>(e->Xq),
+                  e->tc ? reinterpret_cast<bf16*>(e->Xq) : nullptr, B, T, P, d, s));
+  float* lg = logits_out ? logits_out : e->logits;
+  GemmEpi bp;
+  bp.bias = WF(e, "decoder.bbox_proj.bias"); bp.out_f32 = lg; bp.ldo = pp8;
+  CK(linear(e, e->Xq, "decoder.bbox_proj.weight", B * P, pp8, d, EPI_F32, bp, s));
+  CK(unpatchify_sigmoid(lg, heat_out, B, 8, e->S, e->patch, s));
+  return BD_OK;
+}
+
+extern "C" int bd_dino_forward(bd_handle e, const void* images, int32_t dtype, float* feats_out, int32_t L, void* stream) {
+  if (!e || !images || !feats_out) return fail(BD_ERR_INVALID, "bd_dino_forward: null argument");
+  return dino_forward_impl(e, images, dtype, feats_out, L, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bd_decoder_forward(bd_handle e, const void* bbox_feat, int32_t dtype, const float* feats, const int64_t* query_idx,
+                                  float* heat_out, float* logits_out, int32_t B, int32_t T, void* stream) {
+  if (!e || !bbox_feat || !feats || !query_idx || !heat_out) return fail(BD_ERR_INVALID, "bd_decoder_forward: null argument");
+  return decoder_forward_impl(e, bbox_feat, dtype, feats, false, query_idx, heat_out, logits_out, B, T,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bd_corners_topk(bd_handle e, const float* heat, float* corners_px, float* corners_norm, int32_t* idx_out, int32_t B,
+                               int32_t S, void* stream) {
+  (void)e;
+  if (!heat || !corners_px || !corners_norm) return fail(BD_ERR_INVALID, "bd_corners_topk: null argument");
+  if (B < 0 || S <= 0) return fail(BD_ERR_INVALID, "bd_corners_topk: bad shape");
+  CK(corners_topk(heat, corners_px, corners_norm, idx_out, B, 8, S, reinterpret_cast<cudaStream_t>(stream)));
+  return BD_OK;
+}
+
+static PnpOpts to_opts(const bd_pnp_opts* o) {
+  PnpOpts p{0, 0, 1.0f, 0u, 100};
+  if (o) { p.mode = o->mode; p.n_hyp = o->n_hyp; p.thr_px = o->thr_px; p.seed = o->seed; p.max_iter = o->max_iter; }
+  return p;
+}
+
+extern "C" int bd_pnp(bd_handle e, const float* corners_px, const float* bbox3d, const float* K, float* poses_out,
+                      const bd_pnp_opts* opts, int32_t B, int32_t n_pts, void* stream) {
+  (void)e;
+  if (!corners_px || !bbox3d || !K || !poses_out) return fail(BD_ERR_INVALID, "bd_pnp: null argument");
+  cudaError_t ce = pnp_solve(corners_px, bbox3d, K, poses_out, to_opts(opts), B, n_pts, reinterpret_cast<cudaStream_t>(stream));
+  if (ce == cudaErrorNotSupported) return fail(BD_ERR_UNSUPPORTED, "bd_pnp: mode not built");
+  if (ce == cudaErrorInvalidValue) return fail(BD_ERR_INVALID, "bd_pnp: n_pts must be in [6,16]");
+  CK(ce);
+  return BD_OK;
+}
+
+extern "C" int bd_forward(bd_handle e, const void* images, const void* bbox_feat, int32_t in_dtype, const int64_t* query_idx,
+                          const float* bbox3d_q, const float* K_q, float* heat_out, float* corners_px, float* corners_norm,
+                          float* poses_out, const bd_pnp_opts* opts, int32_t B, int32_t T, void* stream) {
+  if (!e || !images || !bbox_feat || !query_idx || !bbox3d_q || !K_q || !corners_px || !corners_norm || !poses_out)
+    return fail(BD_ERR_INVALID, "bd_forward: null argument");
+  if (B <= 0 || T <= 0 || B > e->Bmax || T > e->Tmax) return fail(BD_ERR_INVALID, "bd_forward: B/T exceed the workspace");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  float* heat = heat_out ? heat_out : e->heat;
+  int r = dino_forward_impl(e, images, in_dtype, e->feats, B * T, s);
+  if (r != BD_OK) return r;
+  r = decoder_forward_impl(e, bbox_feat, in_dtype, e->feats, e->tc, query_idx, heat, nullptr, B, T, s);
+  if (r != BD_OK) return r;
+  CK(corners_topk(heat, corners_px, corners_norm, nullptr, B, 8, e->S, s));
+  cudaError_t ce = pnp_solve(corners_px, bbox3d_q, K_q, poses_out, to_opts(opts), B, 8, s);
+  if (ce == cudaErrorNotSupported) return fail(BD_ERR_UNSUPPORTED, "bd_forward: pnp mode not built");
+  CK(ce);
+  return BD_OK;
+}
+
+extern "C" int bd_forward_host(bd_handle e, const void* images_host, const void* bbox_feat_host, int32_t in_dtype,
+                               const int64_t* query_idx_host, const float* bbox3d_q_host, const float* K_q_host,
+                               float* heat_out_host, float* corners_px_host, float* corners_norm_host, float* poses_out_host,
+                               const bd_pnp_opts* opts, int32_t B, int32_t T) {
+  if (!e || !images_host || !bbox_feat_host || !query_idx_host || !bbox3d_q_host || !K_q_host || !corners_px_host ||
+      !corners_norm_host || !poses_out_host)
+    return fail(BD_ERR_INVALID, "bd_forward_host: null argument");
+  if (B <= 0 || T <= 0 || B > e->Bmax || T > e->Tmax) return fail(BD_ERR_INVALID, "bd_forward_host: B/T exceed the workspace");
+  const size_t es = in_dtype == BD_BF16 ? 2 : 4;
+  const size_t SS = static_cast<size_t>(e->S) * e->S;
+  if (!e->in_images) {
+    const size_t Lm = e->Lmax;
+    DALLOC(e->in_images, Lm * 3 * SS * 4);
+    DALLOC(e->in_bbox, Lm * 8 * SS * 4);
+    CK(cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking));
+  }
+  cudaStream_t s = e->host_stream;
+  const size_t L = static_cast<size_t>(B) * T;
+  CK(cudaMemcpyAsync(e->in_images, images_host, L * 3 * SS * es, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->in_bbox, bbox_feat_host, L * 8 * SS * es, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->qidx, query_idx_host, static_cast<size_t>(B) * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->bbox3d_q, bbox3d_q_host, static_cast<size_t>(B) * 24 * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->K_q, K_q_host, static_cast<size_t>(B) * 9 * 4, cudaMemcpyHostToDevice, s));
+  int r = bd_forward(e, e->in_images, e->in_bbox, in_dtype, e->qidx, e->bbox3d_q, e->K_q, e->heat, e->corners_px, e->corners_norm,
+                     e->poses, opts, B, T, s);
+  if (r != BD_OK) return r;
+  CK(cudaMemcpyAsync(corners_px_host, e->corners_px, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(corners_norm_host, e->corners_norm, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(poses_out_host, e->poses, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToHost, s));
+  if (heat_out_host) CK(cudaMemcpyAsync(heat_out_host, e->heat, static_cast<size_t>(B) * 8 * SS * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return BD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel-level entry points
+
+extern "C" int bd_gemm(const void* A, const void* W, const float* bias, const float* gamma, void* out, int32_t M, int32_t N,
+                       int32_t K, int32_t epilogue, int32_t precision, void* stream) {
+  if (!A || !W || !bias || !out) return fail(BD_ERR_INVALID, "bd_gemm: null argument");
+  if (epilogue != EPI_F32 && epilogue != EPI_GELU && epilogue != EPI_RESID && epilogue != EPI_ACT)
+    return fail(BD_ERR_INVALID, "bd_gemm: epilogue must be 0, 1, 2 or 4");
+  GemmEpi e;
+  e.bias = bias; e.gamma = gamma; e.ldo = N;
+  if (epilogue == EPI_F32 || epilogue == EPI_RESID) e.out_f32 = reinterpret_cast<float*>(out);
+  else e.out_act = out;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (precision == BD_PRECISION_BF16)
+    CK(gemm_tc(reinterpret_cast<const bf16*>(A), reinterpret_cast<const bf16*>(W), M, N, K, epilogue, e, s));
+  else
+    CK(gemm_f32(reinterpret_cast<const float*>(A), reinterpret_cast<const float*>(W), M, N, K, epilogue, e, s));
+  return BD_OK;
+}
+
+extern "C" int bd_qkv_project(const void* x, const void* W, const float* bias, const float* q_norm_w, const float* k_norm_w,
+                              void* Q, void* K, void* V, void* scratch, int32_t L, int32_t seq, int32_t seq_pad, int32_t heads,
+                              int32_t head_dim, int32_t precision, void* stream) {
+  if (!x || !W || !bias || !Q || !K || !V) return fail(BD_ERR_INVALID, "bd_qkv_project: null argument");
+  GemmEpi e;
+  e.bias = bias; e.q = Q; e.k = K; e.v = V; e.q_norm_w = q_norm_w; e.k_norm_w = k_norm_w;
+  e.seq = seq; e.seq_pad = seq_pad; e.heads = heads; e.head_dim = head_dim; e.rms_eps = 1e-6f;
+  const int d = heads * head_dim;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (precision == BD_PRECISION_BF16) {
+    CK(gemm_tc(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(W), L * seq, 3 * d, d, EPI_QKV, e, s));
+  } else {
+    if (!scratch) return fail(BD_ERR_INVALID, "bd_qkv_project: exact path needs scratch");
+    e.out_act = scratch;
+    CK(gemm_f32(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(W), L * seq, 3 * d, d, EPI_QKV, e, s));
+  }
+  return BD_OK;
+}
+
+extern "C" int bd_attention(const void* Q, const void* K, const void* V, void* O, int32_t L, int32_t heads, int32_t head_dim,
+                            int32_t seq, int32_t seq_pad, float scale, int32_t precision, int32_t variant, void* stream) {
+  if (!Q || !K || !V || !O) return fail(BD_ERR_INVALID, "bd_attention: null argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (precision == BD_PRECISION_BF16)
+    CK(attention_tc(reinterpret_cast<const bf16*>(Q), reinterpret_cast<const bf16*>(K), reinterpret_cast<const bf16*>(V),
+                    reinterpret_cast<bf16*>(O), L, heads, head_dim, seq, seq_pad, scale, variant, s));
+  else
+    CK(attention_f32(reinterpret_cast<const float*>(Q), reinterpret_cast<const float*>(K), reinterpret_cast<const float*>(V),
+                     reinterpret_cast<float*>(O), L, heads, head_dim, seq, seq_pad, scale, s));
+  return BD_OK;
+}
+
+extern "C" int bd_layernorm(const float* x, const float* w, const float* b, float eps, float* out_f32, void* out_bf16, int32_t rows,
+                            int32_t d, void* stream) {
+  if (!x || (!out_f32 && !out_bf16)) return fail(BD_ERR_INVALID, "bd_layernorm: null argument");
+  CK(layernorm(x, w, b, eps, out_f32, reinterpret_cast<bf16*>(out_bf16), rows, d, 0, 0, 0, reinterpret_cast<cudaStream_t>(stream)));
+  return BD_OK;
+}

@@ -1,0 +1,418 @@
+// fp32 "exact" compute path (SIMT GEMM + attention, used for the parity gate against the fp32 oracle)
+// and the memory-bound glue kernels shared by both precision modes (LayerNorm, im2col, patchify,
+// token fusion, query gather, unpatchify + sigmoid).
+#include "bd_internal.h"
+
+namespace bd {
+
+// ---------------------------------------------------------------------------------------------
+// fp32 SIMT GEMM: out = epi(A[M,K] . W[N,K]^T + bias)
+
+static constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
+
+__device__ __forceinline__ float gelu_erf_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int EPI>
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, int M, int N,
+                                                       int K, GemmEpi e) {
+  __shared__ float As[SG_BK][SG_BM + 4];
+  __shared__ float Bs[SG_BK][SG_BN + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int lr = threadIdx.x >> 2;        // 0..63 tile row
+  const int lk = (threadIdx.x & 3) * 4;   // 0,4,8,12
+  for (int k0 = 0; k0 < K; k0 += SG_BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + lk + i;
+      const int ra = m0 + lr, rb = n0 + lr;
+      As[lk + i][lr] = (ra < M && k < K) ? A[static_cast<long long>(ra) * K + k] : 0.f;
+      Bs[lk + i][lr] = (rb < N && k < K) ? W[static_cast<long long>(rb) * K + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      const float v = acc[i][j] + e.bias[n];
+      if constexpr (EPI == EPI_F32) {
+        long long orow = m;
+        float add = 0.f;
+        if (e.rp_in > 0) {
+          const int tr = m % e.rp_in;
+          orow = static_cast<long long>(m / e.rp_in) * e.rp_out + e.rp_off + tr;
+          if (e.addtab) add = e.addtab[static_cast<long long>(tr) * N + n];
+        }
+        e.out_f32[orow * e.ldo + n] = v + add;
+      } else if constexpr (EPI == EPI_RESID) {
+        float* dst = e.out_f32 + static_cast<long long>(m) * e.ldo + n;
+        const float g = e.gamma ? e.gamma[n] : 1.f;
+        *dst = *dst + g * v;
+      } else if constexpr (EPI == EPI_GELU) {
+        reinterpret_cast<float*>(e.out_act)[static_cast<long long>(m) * N + n] = gelu_erf_exact(v);
+      } else {
+        reinterpret_cast<float*>(e.out_act)[static_cast<long long>(m) * N + n] = v;
+      }
+    }
+  }
+}
+
+__global__ void qkv_split_f32_kernel(const float* __restrict__ qkv, GemmEpi e, int M) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int per_row = 3 * e.heads;
+  if (idx >= static_cast<long long>(M) * per_row) return;
+  const int m = static_cast<int>(idx / per_row);
+  const int wh = static_cast<int>(idx % per_row);
+  const int which = wh / e.heads, head = wh % e.heads;
+  const int hd = e.head_dim, d = e.heads * hd;
+  const float* src = qkv + static_cast<long long>(m) * 3 * d + which * d + head * hd;
+  const int l = m / e.seq, tok = m % e.seq;
+  float* dst = reinterpret_cast<float*>(which == 0 ? e.q : (which == 1 ? e.k : e.v)) +
+               ((static_cast<long long>(l) * e.heads + head) * e.seq_pad + tok) * hd;
+  const float* nw = which == 0 ? e.q_norm_w : (which == 1 ? e.k_norm_w : nullptr);
+  if (nw != nullptr) {
+    float ss = 0.f;
+    for (int j = 0; j < hd; ++j) ss = fmaf(src[j], src[j], ss);
+    const float r = rsqrtf(ss / hd + e.rms_eps);
+    for (int j = 0; j < hd; ++j) dst[j] = nw[j] * (src[j] * r);
+  } else {
+    for (int j = 0; j < hd; ++j) dst[j] = src[j];
+  }
+}
+
+cudaError_t qkv_split_f32(const float* qkv, const GemmEpi& e, int M, cudaStream_t s) {
+  const long long n = static_cast<long long>(M) * 3 * e.heads;
+  qkv_split_f32_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, s>>>(qkv, e, M);
+  return cudaGetLastError();
+}
+
+cudaError_t gemm_f32(const float* A, const float* W, int M, int N, int K, int epi, const GemmEpi& e, cudaStream_t s) {
+  dim3 grid((N + SG_BN - 1) / SG_BN, (M + SG_BM - 1) / SG_BM);
+  switch (epi) {
+    case EPI_F32: gemm_f32_kernel<EPI_F32><<<grid, 256, 0, s>>>(A, W, M, N, K, e); break;
+    case EPI_RESID: gemm_f32_kernel<EPI_RESID><<<grid, 256, 0, s>>>(A, W, M, N, K, e); break;
+    case EPI_GELU: gemm_f32_kernel<EPI_GELU><<<grid, 256, 0, s>>>(A, W, M, N, K, e); break;
+    case EPI_ACT: gemm_f32_kernel<EPI_ACT><<<grid, 256, 0, s>>>(A, W, M, N, K, e); break;
+    case EPI_QKV: {
+      // raw qkv into the caller-provided scratch (e.out_act, [M, 3d] fp32), then norm + split
+      gemm_f32_kernel<EPI_ACT><<<grid, 256, 0, s>>>(A, W, M, N, K, e);
+      cudaError_t err = cudaGetLastError();
+      if (err != cudaSuccess) return err;
+      return qkv_split_f32(reinterpret_cast<const float*>(e.out_act), e, M, s);
+    }
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 attention: one CTA per (query row, bh)
+
+__global__ void __launch_bounds__(128) attention_f32_kernel(const float* __restrict__ Q, const float* __restrict__ K,
+                                                            const float* __restrict__ V, float* __restrict__ O, int heads,
+                                                            int hd, int seq, int seq_pad, float scale) {
+  extern __shared__ float sm[];
+  float* sc = sm;            // [seq]
+  float* qs = sm + seq;      // [hd]
+  __shared__ float red[4];
+  const int row = blockIdx.x, bh = blockIdx.y;
+  const int tid = threadIdx.x;
+  const float* q = Q + (static_cast<long long>(bh) * seq_pad + row) * hd;
+  for (int j = tid; j < hd; j += 128) qs[j] = q[j] * scale;
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int key = tid; key < seq; key += 128) {
+    const float* kp = K + (static_cast<long long>(bh) * seq_pad + key) * hd;
+    float s = 0.f;
+    for (int j = 0; j < hd; ++j) s = fmaf(qs[j], kp[j], s);
+    sc[key] = s;
+    mx = fmaxf(mx, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int key = tid; key < seq; key += 128) {
+    const float p = expf(sc[key] - mx);
+    sc[key] = p;
+    sum += p;
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((tid & 31) == 0) red[tid >> 5] = sum;
+  __syncthreads();
+  sum = red[0] + red[1] + red[2] + red[3];
+  const float inv = 1.0f / sum;
+  const int l = bh / heads, head = bh % heads;
+  for (int j = tid; j < hd; j += 128) {
+    float acc = 0.f;
+    const float* vp = V + static_cast<long long>(bh) * seq_pad * hd + j;
+    for (int key = 0; key < seq; ++key) acc = fmaf(sc[key], vp[static_cast<long long>(key) * hd], acc);
+    O[(static_cast<long long>(l) * seq + row) * (heads * hd) + head * hd + j] = acc * inv;
+  }
+}
+
+cudaError_t attention_f32(const float* Q, const float* K, const float* V, float* O, int L, int heads, int head_dim, int seq,
+                          int seq_pad, float scale, cudaStream_t s) {
+  const size_t smem = (static_cast<size_t>(seq) + head_dim) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+  }
+  dim3 grid(seq, L * heads);
+  attention_f32_kernel<<<grid, 128, smem, s>>>(Q, K, V, O, heads, head_dim, seq, seq_pad, scale);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm (one warp per row)
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, float eps, float* __restrict__ out_f32,
+                                                        bf16* __restrict__ out_bf16, int rows_out, int d, int rows_out_per,
+                                                        int rows_in_per, int row_off) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows_out) return;
+  long long rin = r;
+  if (rows_out_per > 0) rin = static_cast<long long>(r / rows_out_per) * rows_in_per + row_off + (r % rows_out_per);
+  const float* xr = x + rin * d;
+  float sum = 0.f;
+  for (int j = lane; j < d; j += 32) sum += xr[j];
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / d;
+  float var = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const float t = xr[j] - mean;
+    var = fmaf(t, t, var);
+  }
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / d + eps);
+  for (int j = lane; j < d; j += 32) {
+    float v = (xr[j] - mean) * rstd;
+    if (w) v = v * w[j] + b[j];
+    if (out_f32) out_f32[static_cast<long long>(r) * d + j] = v;
+    if (out_bf16) out_bf16[static_cast<long long>(r) * d + j] = __float2bfloat16_rn(v);
+  }
+}
+
+cudaError_t layernorm(const float* x, const float* w, const float* b, float eps, float* out_f32, bf16* out_bf16, int rows_out,
+                      int d, int rows_out_per, int rows_in_per, int row_off, cudaStream_t s) {
+  layernorm_kernel<<<(rows_out + 7) / 8, 256, 0, s>>>(x, w, b, eps, out_f32, out_bf16, rows_out, d, rows_out_per, rows_in_per,
+                                                      row_off);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// im2col for the 14x14/s14 patch-embed conv with the ImageNet normalisation folded in
+// (encoder/dinov2.py:45-46, DINOv2 layers/patch_embed.py:65-78).  Column order (c, pr, pc) = conv weight order.
+
+template <typename TIn, typename TOut>
+__global__ void im2col_kernel(const TIn* __restrict__ img, TOut* __restrict__ out, int L, int S, int patch, int kpad) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int g = S / patch;
+  const long long total = static_cast<long long>(L) * g * g * kpad;
+  if (idx >= total) return;
+  const int col = static_cast<int>(idx % kpad);
+  const long long rowi = idx / kpad;
+  const int kreal = 3 * patch * patch;
+  float v = 0.f;
+  if (col < kreal) {
+    const int c = col / (patch * patch), rem = col % (patch * patch);
+    const int pr = rem / patch, pc = rem % patch;
+    const int pw = static_cast<int>(rowi % g), ph = static_cast<int>((rowi / g) % g);
+    const long long l = rowi / (g * g);
+    const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+    const float stdv = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+    const float x = static_cast<float>(img[((l * 3 + c) * S + ph * patch + pr) * S + pw * patch + pc]);
+    v = (x - mean) / stdv;
+  }
+  out[idx] = static_cast<TOut>(v);
+}
+
+cudaError_t im2col_patches(const void* images, int img_is_bf16, void* out, int out_is_bf16, int L, int S, int patch, int kpad,
+                           cudaStream_t s) {
+  const int g = S / patch;
+  const long long total = static_cast<long long>(L) * g * g * kpad;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (img_is_bf16 && out_is_bf16)
+    im2col_kernel<bf16, bf16><<<blocks, 256, 0, s>>>(reinterpret_cast<const bf16*>(images), reinterpret_cast<bf16*>(out), L, S, patch, kpad);
+  else if (img_is_bf16)
+    im2col_kernel<bf16, float><<<blocks, 256, 0, s>>>(reinterpret_cast<const bf16*>(images), reinterpret_cast<float*>(out), L, S, patch, kpad);
+  else if (out_is_bf16)
+    im2col_kernel<float, bf16><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(images), reinterpret_cast<bf16*>(out), L, S, patch, kpad);
+  else
+    im2col_kernel<float, float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(images), reinterpret_cast<float*>(out), L, S, patch, kpad);
+  return cudaGetLastError();
+}
+
+// patchify of the 8-channel corner heatmaps (betr.py:211-228): per-token feature order (pr, pc, c)
+template <typename TIn, typename TOut>
+__global__ void patchify_kernel(const TIn* __restrict__ feat, TOut* __restrict__ out, int L, int C, int S, int patch) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int g = S / patch;
+  const int kk = patch * patch * C;
+  const long long total = static_cast<long long>(L) * g * g * kk;
+  if (idx >= total) return;
+  const int col = static_cast<int>(idx % kk);
+  const long long rowi = idx / kk;
+  const int c = col % C, pp = col / C;
+  const int pr = pp / patch, pc = pp % patch;
+  const int pw = static_cast<int>(rowi % g), ph = static_cast<int>((rowi / g) % g);
+  const long long l = rowi / (g * g);
+  out[idx] = static_cast<TOut>(static_cast<float>(feat[((l * C + c) * S + ph * patch + pr) * S + pw * patch + pc]));
+}
+
+cudaError_t patchify_heat(const void* feat, int in_is_bf16, void* out, int out_is_bf16, int L, int C, int S, int patch,
+                          cudaStream_t s) {
+  const int g = S / patch;
+  const long long total = static_cast<long long>(L) * g * g * patch * patch * C;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (in_is_bf16 && out_is_bf16)
+    patchify_kernel<bf16, bf16><<<blocks, 256, 0, s>>>(reinterpret_cast<const bf16*>(feat), reinterpret_cast<bf16*>(out), L, C, S, patch);
+  else if (in_is_bf16)
+    patchify_kernel<bf16, float><<<blocks, 256, 0, s>>>(reinterpret_cast<const bf16*>(feat), reinterpret_cast<float*>(out), L, C, S, patch);
+  else if (out_is_bf16)
+    patchify_kernel<float, bf16><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(feat), reinterpret_cast<bf16*>(out), L, C, S, patch);
+  else
+    patchify_kernel<float, float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(feat), reinterpret_cast<float*>(out), L, C, S, patch);
+  return cudaGetLastError();
+}
+
+// DINOv2 prepare_tokens (vision_transformer.py:213-232): row 0 = cls + pos[0]; rows 1..n_reg = register tokens
+__global__ void dino_prefix_kernel(float* __restrict__ X, const float* __restrict__ cls, const float* __restrict__ pos0,
+                                   const float* __restrict__ reg, int L, int n_tok, int n_reg, int d) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(L) * (1 + n_reg) * d;
+  if (idx >= total) return;
+  const int j = static_cast<int>(idx % d);
+  const int t = static_cast<int>((idx / d) % (1 + n_reg));
+  const long long l = idx / (static_cast<long long>(d) * (1 + n_reg));
+  const float v = (t == 0) ? (cls[j] + pos0[j]) : reg[(t - 1) * d + j];
+  X[(l * n_tok + t) * d + j] = v;
+}
+
+cudaError_t dino_prefix_tokens(float* X, const float* cls, const float* pos0, const float* reg, int L, int n_tok, int n_reg,
+                               int d, cudaStream_t s) {
+  const long long total = static_cast<long long>(L) * (1 + n_reg) * d;
+  dino_prefix_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(X, cls, pos0, reg, L, n_tok, n_reg, d);
+  return cudaGetLastError();
+}
+
+// BETR token fusion (betr.py:282-295, 351-401): one warp per token
+__global__ void __launch_bounds__(256) betr_fuse_kernel(const float* __restrict__ PF, const float* __restrict__ R,
+                                                        const float* __restrict__ qtok, const float* __restrict__ pos,
+                                                        const int64_t* __restrict__ qidx, float* __restrict__ X, int B, int T,
+                                                        int P, int d, float eps) {
+  const long long m = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (m >= static_cast<long long>(B) * T * P) return;
+  const int p = static_cast<int>(m % P);
+  const int t = static_cast<int>((m / P) % T);
+  const int b = static_cast<int>(m / (static_cast<long long>(P) * T));
+  const bool is_q = (qidx[b] == t);
+  const float* rr = R + m * d;
+  float sum = 0.f;
+  for (int j = lane; j < d; j += 32) sum += rr[j];
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / d;
+  float var = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const float tt = rr[j] - mean;
+    var = fmaf(tt, tt, var);
+  }
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / d + eps);
+  const float* pf = is_q ? qtok : (PF + m * d);
+  for (int j = lane; j < d; j += 32) {
+    const float rgb = (rr[j] - mean) * rstd;
+    X[m * d + j] = (pf[j] + rgb) + pos[static_cast<long long>(p) * d + j];
+  }
+}
+
+cudaError_t betr_fuse(const float* PF, const float* R, const float* query_tok, const float* pos, const int64_t* query_idx,
+                      float* X, int B, int T, int P, int d, float eps, cudaStream_t s) {
+  const long long rows = static_cast<long long>(B) * T * P;
+  betr_fuse_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(PF, R, query_tok, pos, query_idx, X, B, T, P, d, eps);
+  return cudaGetLastError();
+}
+
+__global__ void gather_query_kernel(const float* __restrict__ X, const int64_t* __restrict__ qidx, float* __restrict__ of,
+                                    bf16* __restrict__ ob, int B, int T, int P, int d) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * P * d;
+  if (idx >= total) return;
+  const int j = static_cast<int>(idx % d);
+  const int p = static_cast<int>((idx / d) % P);
+  const int b = static_cast<int>(idx / (static_cast<long long>(d) * P));
+  const float v = X[((static_cast<long long>(b) * T + qidx[b]) * P + p) * d + j];
+  if (of) of[idx] = v;
+  if (ob) ob[idx] = __float2bfloat16_rn(v);
+}
+
+cudaError_t gather_query(const float* X, const int64_t* query_idx, float* out_f32, bf16* out_bf16, int B, int T, int P, int d,
+                         cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * P * d;
+  gather_query_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(X, query_idx, out_f32, out_bf16, B, T, P, d);
+  return cudaGetLastError();
+}
+
+// unpatchify (betr.py:230-247) + sigmoid + 2x-1 (betr.py:432-435)
+__global__ void unpatchify_sigmoid_kernel(const float* __restrict__ logits, float* __restrict__ heat, int B, int C, int S,
+                                          int patch) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * C * S * S;
+  if (idx >= total) return;
+  const int x = static_cast<int>(idx % S);
+  const int y = static_cast<int>((idx / S) % S);
+  const int c = static_cast<int>((idx / (static_cast<long long>(S) * S)) % C);
+  const long long b = idx / (static_cast<long long>(S) * S * C);
+  const int g = S / patch;
+  const int tok = (y / patch) * g + (x / patch);
+  const int j = ((y % patch) * patch + (x % patch)) * C + c;
+  const float l = logits[(b * g * g + tok) * (static_cast<long long>(patch) * patch * C) + j];
+  const float sg = 1.0f / (1.0f + expf(-l));
+  heat[idx] = 2.0f * sg - 1.0f;
+}
+
+cudaError_t unpatchify_sigmoid(const float* logits, float* heat, int B, int C, int S, int patch, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * C * S * S;
+  unpatchify_sigmoid_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(logits, heat, B, C, S, patch);
+  return cudaGetLastError();
+}
+
+__global__ void cast_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx < n) out[idx] = __float2bfloat16_rn(in[idx]);
+}
+
+cudaError_t cast_f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t s) {
+  cast_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(in, out, n);
+  return cudaGetLastError();
+}
+
+}  // namespace bd

@@ -1,0 +1,378 @@
+// Corner extraction (top-20 mean) and PnP pose solve on the device: no .cpu() sync, no cv2 call.
+//   corners_topk  <- recover_bb8_corners, heatmap branch (src/models/utils/box_utils.py:75-110)
+//   pnp_solve     <- cv2.solvePnP(SOLVEPNP_ITERATIVE) + cv2.Rodrigues as used at box_utils.py:171-192
+#include <limits.h>
+
+#include "bd_internal.h"
+
+namespace bd {
+
+// ---------------------------------------------------------------------------------------------
+// top-20 over one S*S heat map per CTA.  HBM-bound: every pixel is read exactly once (coalesced),
+// each thread keeps a sorted top-20 of its strided slice in registers, then 20 block-argmax rounds merge.
+// Order: larger (x+1)/2 first, ties -> lower flat index (torch.topk leaves ties unspecified).
+
+static constexpr int TOPK = 20;
+static constexpr int TK_THREADS = 256;
+
+__device__ __forceinline__ bool tk_better(float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); }
+
+__global__ void __launch_bounds__(TK_THREADS) corners_topk_kernel(const float* __restrict__ heat, float* __restrict__ corners_px,
+                                                                  float* __restrict__ corners_norm, int32_t* __restrict__ idx_out,
+                                                                  int S) {
+  const int map = blockIdx.x;
+  const int n = S * S;
+  const float* hm = heat + static_cast<long long>(map) * n;
+  float val[TOPK];
+  int idx[TOPK];
+#pragma unroll
+  for (int k = 0; k < TOPK; ++k) { val[k] = -INFINITY; idx[k] = INT_MAX; }
+  for (int i = threadIdx.x; i < n; i += TK_THREADS) {
+    const float v = (__ldg(hm + i) + 1.0f) * 0.5f;  // box_utils.py:79
+    if (tk_better(v, i, val[TOPK - 1], idx[TOPK - 1])) {
+      val[TOPK - 1] = v;
+      idx[TOPK - 1] = i;
+#pragma unroll
+      for (int k = TOPK - 1; k > 0; --k) {
+        if (tk_better(val[k], idx[k], val[k - 1], idx[k - 1])) {
+          const float tv = val[k]; val[k] = val[k - 1]; val[k - 1] = tv;
+          const int ti = idx[k]; idx[k] = idx[k - 1]; idx[k - 1] = ti;
+        }
+      }
+    }
+  }
+  __shared__ float s_val[TK_THREADS / 32];
+  __shared__ int s_idx[TK_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int sum_x = 0, sum_y = 0;
+  for (int round = 0; round < TOPK; ++round) {
+    float bv = val[0];
+    int bi = idx[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (tk_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
+    __syncthreads();
+    bv = s_val[0]; bi = s_idx[0];
+#pragma unroll
+    for (int w = 1; w < TK_THREADS / 32; ++w) {
+      if (tk_better(s_val[w], s_idx[w], bv, bi)) { bv = s_val[w]; bi = s_idx[w]; }
+    }
+    __syncthreads();
+    if (idx[0] == bi) {  // the unique owner pops its head
+#pragma unroll
+      for (int k = 0; k < TOPK - 1; ++k) { val[k] = val[k + 1]; idx[k] = idx[k + 1]; }
+      val[TOPK - 1] = -INFINITY; idx[TOPK - 1] = INT_MAX;
+    }
+    sum_x += bi % S;   // box_utils.py:90-91
+    sum_y += bi / S;
+    if (threadIdx.x == 0 && idx_out) idx_out[static_cast<long long>(map) * TOPK + round] = bi;
+  }
+  if (threadIdx.x == 0) {
+    const float x = static_cast<float>(sum_x) / static_cast<float>(TOPK);  // mean of exact integers
+    const float y = static_cast<float>(sum_y) / static_cast<float>(TOPK);
+    corners_px[map * 2 + 0] = x;
+    corners_px[map * 2 + 1] = y;
+    corners_norm[map * 2 + 0] = (x / static_cast<float>(S)) * 2.0f - 1.0f;  // box_utils.py:104-108
+    corners_norm[map * 2 + 1] = (y / static_cast<float>(S)) * 2.0f - 1.0f;
+  }
+}
+
+cudaError_t corners_topk(const float* heat, float* corners_px, float* corners_norm, int32_t* idx_out, int B, int C, int S,
+                         cudaStream_t s) {
+  if (B * C <= 0) return cudaSuccess;
+  corners_topk_kernel<<<B * C, TK_THREADS, 0, s>>>(heat, corners_px, corners_norm, idx_out, S);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// PnP, reference-parity mode: DLT on all points (normalised image coordinates, smallest eigenvector of
+// A^T A by cyclic Jacobi) -> nearest rotation (Newton polar iteration) -> Levenberg-Marquardt on the pixel
+// reprojection error over all points, run to convergence, all in fp64.  One thread per query.
+
+static constexpr int PNP_MAXPTS = 16;
+
+__device__ void jacobi_eig_sym12(double (&A)[12][12], double (&V)[12][12]) {
+  for (int i = 0; i < 12; ++i)
+    for (int j = 0; j < 12; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int i = 0; i < 12; ++i) {
+      dg += A[i][i] * A[i][i];
+      for (int j = i + 1; j < 12; ++j) off += A[i][j] * A[i][j];
+    }
+    if (off <= 1e-60 * dg || off == 0.0) break;
+    for (int p = 0; p < 11; ++p) {
+      for (int q = p + 1; q < 12; ++q) {
+        const double apq = A[p][q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 12; ++k) {
+          const double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - s * akq;
+          A[k][q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 12; ++k) {
+          const double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - s * aqk;
+          A[q][k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 12; ++k) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq;
+          V[k][q] = s * vkp + c * vkq;
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ double det3(const double (&R)[3][3]) {
+  return R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
+         R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+}
+
+// orthogonal polar factor by Newton iteration R <- (R + R^-T)/2
+__device__ void nearest_rotation(double (&R)[3][3], int iters) {
+  for (int it = 0; it < iters; ++it) {
+    const double d = det3(R);
+    if (fabs(d) < 1e-300) return;
+    double C[3][3];  // cofactor matrix = det * R^-T
+    C[0][0] = R[1][1] * R[2][2] - R[1][2] * R[2][1];
+    C[0][1] = R[1][2] * R[2][0] - R[1][0] * R[2][2];
+    C[0][2] = R[1][0] * R[2][1] - R[1][1] * R[2][0];
+    C[1][0] = R[0][2] * R[2][1] - R[0][1] * R[2][2];
+    C[1][1] = R[0][0] * R[2][2] - R[0][2] * R[2][0];
+    C[1][2] = R[0][1] * R[2][0] - R[0][0] * R[2][1];
+    C[2][0] = R[0][1] * R[1][2] - R[0][2] * R[1][1];
+    C[2][1] = R[0][2] * R[1][0] - R[0][0] * R[1][2];
+    C[2][2] = R[0][0] * R[1][1] - R[0][1] * R[1][0];
+    double delta = 0.0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        const double nv = 0.5 * (R[i][j] + C[i][j] / d);
+        delta += (nv - R[i][j]) * (nv - R[i][j]);
+        R[i][j] = nv;
+      }
+    if (delta < 1e-32) break;
+  }
+}
+
+__device__ void rodrigues_exp(const double (&w)[3], double (&E)[3][3]) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const double th = sqrt(th2);
+  double a, b;  // E = I + a K + b K^2
+  if (th < 1e-12) { a = 1.0; b = 0.0; }
+  else { a = sin(th) / th; b = (1.0 - cos(th)) / th2; }
+  const double K[3][3] = {{0, -w[2], w[1]}, {w[2], 0, -w[0]}, {-w[1], w[0], 0}};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double k2 = 0.0;
+      for (int k = 0; k < 3; ++k) k2 += K[i][k] * K[k][j];
+      E[i][j] = (i == j ? 1.0 : 0.0) + a * K[i][j] + b * k2;
+    }
+}
+
+// solve (H + lam*diag(H)) x = -g by Gaussian elimination with partial pivoting; false if singular
+__device__ bool solve6(const double (&H)[6][6], const double (&g)[6], double lam, double (&x)[6]) {
+  double M[6][7];
+  for (int i = 0; i < 6; ++i) {
+    for (int j = 0; j < 6; ++j) M[i][j] = H[i][j] + (i == j ? lam * H[i][i] : 0.0);
+    M[i][6] = -g[i];
+  }
+  for (int c = 0; c < 6; ++c) {
+    int piv = c;
+    double best = fabs(M[c][c]);
+    for (int r = c + 1; r < 6; ++r)
+      if (fabs(M[r][c]) > best) { best = fabs(M[r][c]); piv = r; }
+    if (!(best > 1e-300)) return false;
+    if (piv != c)
+      for (int j = 0; j < 7; ++j) { const double t = M[c][j]; M[c][j] = M[piv][j]; M[piv][j] = t; }
+    for (int r = c + 1; r < 6; ++r) {
+      const double f = M[r][c] / M[c][c];
+      for (int j = c; j < 7; ++j) M[r][j] -= f * M[c][j];
+    }
+  }
+  for (int i = 5; i >= 0; --i) {
+    double sacc = M[i][6];
+    for (int j = i + 1; j < 6; ++j) sacc -= M[i][j] * x[j];
+    x[i] = sacc / M[i][i];
+  }
+  return true;
+}
+
+struct PnpProblem {
+  double X[PNP_MAXPTS][3];
+  double uv[PNP_MAXPTS][2];
+  double fx, fy, cx, cy;
+  int n;
+};
+
+__device__ double reproj_cost(const PnpProblem& pb, const double (&R)[3][3], const double (&t)[3], double (*res)[2],
+                              double (*Xc)[3]) {
+  double cost = 0.0;
+  for (int i = 0; i < pb.n; ++i) {
+    double xc[3];
+    for (int a = 0; a < 3; ++a) xc[a] = R[a][0] * pb.X[i][0] + R[a][1] * pb.X[i][1] + R[a][2] * pb.X[i][2] + t[a];
+    const double ru = pb.fx * xc[0] / xc[2] + pb.cx - pb.uv[i][0];
+    const double rv = pb.fy * xc[1] / xc[2] + pb.cy - pb.uv[i][1];
+    if (res) { res[i][0] = ru; res[i][1] = rv; }
+    if (Xc) { Xc[i][0] = xc[0]; Xc[i][1] = xc[1]; Xc[i][2] = xc[2]; }
+    cost += ru * ru + rv * rv;
+  }
+  return cost;
+}
+
+__device__ void pnp_dlt_init(const PnpProblem& pb, double (&R)[3][3], double (&t)[3]) {
+  double A[12][12], V[12][12];
+  for (int i = 0; i < 12; ++i)
+    for (int j = 0; j < 12; ++j) A[i][j] = 0.0;
+  for (int i = 0; i < pb.n; ++i) {
+    const double xn = (pb.uv[i][0] - pb.cx) / pb.fx, yn = (pb.uv[i][1] - pb.cy) / pb.fy;
+    double r1[12], r2[12];
+    for (int j = 0; j < 12; ++j) { r1[j] = 0.0; r2[j] = 0.0; }
+    for (int a = 0; a < 3; ++a) {
+      r1[a] = pb.X[i][a]; r2[4 + a] = pb.X[i][a];
+      r1[8 + a] = -xn * pb.X[i][a]; r2[8 + a] = -yn * pb.X[i][a];
+    }
+    r1[3] = 1.0; r2[7] = 1.0; r1[11] = -xn; r2[11] = -yn;
+    for (int a = 0; a < 12; ++a)
+      for (int b = 0; b < 12; ++b) A[a][b] += r1[a] * r1[b] + r2[a] * r2[b];
+  }
+  jacobi_eig_sym12(A, V);
+  int kmin = 0;
+  for (int k = 1; k < 12; ++k)
+    if (A[k][k] < A[kmin][kmin]) kmin = k;
+  double Rd[3][3], td[3];
+  for (int a = 0; a < 3; ++a) {
+    for (int b = 0; b < 3; ++b) Rd[a][b] = V[a * 4 + b][kmin];
+    td[a] = V[a * 4 + 3][kmin];
+  }
+  if (det3(Rd) < 0.0) {
+    for (int a = 0; a < 3; ++a) {
+      for (int b = 0; b < 3; ++b) Rd[a][b] = -Rd[a][b];
+      td[a] = -td[a];
+    }
+  }
+  double nrm = 0.0;
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) nrm += Rd[a][b] * Rd[a][b];
+  nrm = sqrt(nrm);
+  const double sc = sqrt(3.0) / fmax(nrm, 1e-300);
+  for (int a = 0; a < 3; ++a) {
+    for (int b = 0; b < 3; ++b) R[a][b] = Rd[a][b] * sc;  // pre-scaled: close to orthogonal already
+    t[a] = td[a] * sc;
+  }
+  nearest_rotation(R, 60);
+}
+
+__device__ void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int max_iter) {
+  double res[PNP_MAXPTS][2], Xc[PNP_MAXPTS][3];
+  double lam = 1e-3;
+  double cost = reproj_cost(pb, R, t, res, Xc);
+  for (int it = 0; it < max_iter; ++it) {
+    double H[6][6], g[6];
+    for (int a = 0; a < 6; ++a) { g[a] = 0.0; for (int b = 0; b < 6; ++b) H[a][b] = 0.0; }
+    for (int i = 0; i < pb.n; ++i) {
+      const double x = Xc[i][0], y = Xc[i][1], z = Xc[i][2];
+      const double du[3] = {pb.fx / z, 0.0, -pb.fx * x / (z * z)};
+      const double dv[3] = {0.0, pb.fy / z, -pb.fy * y / (z * z)};
+      const double Y[3] = {x - t[0], y - t[1], z - t[2]};
+      // d(Xc)/d(omega) = -[Y]_x for the left-multiplicative update R <- exp(omega) R
+      const double W[3][3] = {{0, Y[2], -Y[1]}, {-Y[2], 0, Y[0]}, {Y[1], -Y[0], 0}};
+      double ju[6], jv[6];
+      for (int a = 0; a < 3; ++a) {
+        ju[a] = du[0] * W[0][a] + du[1] * W[1][a] + du[2] * W[2][a];
+        jv[a] = dv[0] * W[0][a] + dv[1] * W[1][a] + dv[2] * W[2][a];
+        ju[3 + a] = du[a];
+        jv[3 + a] = dv[a];
+      }
+      for (int a = 0; a < 6; ++a) {
+        g[a] += ju[a] * res[i][0] + jv[a] * res[i][1];
+        for (int b = 0; b < 6; ++b) H[a][b] += ju[a] * ju[b] + jv[a] * jv[b];
+      }
+    }
+    bool improved = false;
+    double step = 0.0, dc = 0.0;
+    for (int tr = 0; tr < 30; ++tr) {
+      double delta[6];
+      if (!solve6(H, g, lam, delta)) { lam *= 10.0; continue; }
+      const double w[3] = {delta[0], delta[1], delta[2]};
+      double E[3][3], Rn[3][3], tn[3];
+      rodrigues_exp(w, E);
+      for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) Rn[a][b] = E[a][0] * R[0][b] + E[a][1] * R[1][b] + E[a][2] * R[2][b];
+        tn[a] = t[a] + delta[3 + a];
+      }
+      double resn[PNP_MAXPTS][2], Xcn[PNP_MAXPTS][3];
+      const double cn = reproj_cost(pb, Rn, tn, resn, Xcn);
+      if (isfinite(cn) && cn <= cost) {
+        improved = true;
+        step = 0.0;
+        for (int a = 0; a < 6; ++a) step += delta[a] * delta[a];
+        step = sqrt(step);
+        dc = cost - cn;
+        cost = cn;
+        for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) R[a][b] = Rn[a][b]; t[a] = tn[a]; }
+        for (int i = 0; i < pb.n; ++i) {
+          res[i][0] = resn[i][0]; res[i][1] = resn[i][1];
+          Xc[i][0] = Xcn[i][0]; Xc[i][1] = Xcn[i][1]; Xc[i][2] = Xcn[i][2];
+        }
+        lam = fmax(lam * 0.1, 1e-12);
+        break;
+      }
+      lam *= 10.0;
+    }
+    if (!improved || step < 1e-14 || dc <= 1e-30) break;
+  }
+  nearest_rotation(R, 4);
+}
+
+__global__ void __launch_bounds__(64) pnp_iterative_kernel(const float* __restrict__ corners, const float* __restrict__ bbox3d,
+                                                           const float* __restrict__ Kmat, float* __restrict__ poses, int B,
+                                                           int n_pts, int max_iter) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= B) return;
+  PnpProblem pb;
+  pb.n = n_pts;
+  for (int i = 0; i < n_pts; ++i) {
+    for (int a = 0; a < 3; ++a) pb.X[i][a] = static_cast<double>(bbox3d[(static_cast<long long>(q) * n_pts + i) * 3 + a]);
+    for (int a = 0; a < 2; ++a) pb.uv[i][a] = static_cast<double>(corners[(static_cast<long long>(q) * n_pts + i) * 2 + a]);
+  }
+  const float* Kq = Kmat + static_cast<long long>(q) * 9;
+  pb.fx = Kq[0]; pb.fy = Kq[4]; pb.cx = Kq[2]; pb.cy = Kq[5];
+  double R[3][3], t[3];
+  pnp_dlt_init(pb, R, t);
+  pnp_lm(pb, R, t, max_iter);
+  bool ok = true;
+  for (int a = 0; a < 3; ++a) {
+    ok = ok && isfinite(t[a]);
+    for (int b = 0; b < 3; ++b) ok = ok && isfinite(R[a][b]);
+  }
+  float* P = poses + static_cast<long long>(q) * 16;
+  for (int i = 0; i < 16; ++i) P[i] = 0.f;  // failure => zero pose (box_utils.py:136,194-197)
+  if (ok) {
+    for (int a = 0; a < 3; ++a) {
+      for (int b = 0; b < 3; ++b) P[a * 4 + b] = static_cast<float>(R[a][b]);
+      P[a * 4 + 3] = static_cast<float>(t[a]);
+    }
+    P[15] = 1.0f;
+  }
+}
+
+cudaError_t pnp_solve(const float* corners_px, const float* bbox3d, const float* K, float* poses, const PnpOpts& o, int B,
+                      int n_pts, cudaStream_t s) {
+  if (B <= 0) return cudaSuccess;
+  if (n_pts < 6 || n_pts > PNP_MAXPTS) return cudaErrorInvalidValue;
+  if (o.mode != 0) return cudaErrorNotSupported;
+  const int max_iter = o.max_iter > 0 ? o.max_iter : 100;
+  pnp_iterative_kernel<<<(B + 63) / 64, 64, 0, s>>>(corners_px, bbox3d, K, poses, B, n_pts, max_iter);
+  return cudaGetLastError();
+}
+
+}  // namespace bd

@@ -1,0 +1,133 @@
+"""-m gpu: fp32 SIMT kernels and the memory-bound glue kernels, through the C ABI, against torch fp32 / the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from boxdreamer_b200 import _lib, synth
+from gpu_util import gemm, report, sp
+
+pytestmark = pytest.mark.gpu
+EX = _lib.PRECISION_EXACT
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 768, 588), (77, 1568, 768), (256, 768, 3072)])
+def test_gemm_f32_plain(lib, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) * 0.05).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    ref = (A.double() @ W.double().t() + b.double()).float()
+    out = gemm(A, W, b, M, N, K, _lib.EPI_F32, EX)
+    ok, msg = report("gemm_f32", out, ref, tol_rel=2e-6)
+    assert ok, msg
+    out = gemm(A, W, b, M, N, K, _lib.EPI_GELU, EX)
+    ok, msg = report("gemm_f32_gelu", out, F.gelu(ref), tol_rel=3e-6)
+    assert ok, msg
+    res0 = torch.randn(M, N, generator=g).cuda()
+    gam = torch.randn(N, generator=g).cuda()
+    out = gemm(A, W, b, M, N, K, _lib.EPI_RESID, EX, gamma=gam, out=res0.clone())
+    ok, msg = report("gemm_f32_resid", out, res0 + gam * ref, tol_rel=3e-6)
+    assert ok, msg
+
+
+def test_layernorm(lib):
+    x = torch.randn(1000, 768).cuda() * 3 + 1
+    w = torch.randn(768).cuda()
+    b = torch.randn(768).cuda()
+    o32 = torch.empty_like(x)
+    o16 = torch.empty(1000, 768, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.bd_layernorm(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), 1e-5, _lib.ptr(o32), _lib.ptr(o16), 1000, 768, sp()))
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x, (768,), w, b, 1e-5)
+    ok, msg = report("layernorm_f32", o32, ref, tol_abs=2e-5)
+    assert ok, msg
+    ok, msg = report("layernorm_bf16", o16, ref, tol_rel=5e-3)
+    assert ok, msg
+
+
+def test_qkv_project_and_attention_f32(lib):
+    from oracle import boxdreamer_oracle as O
+    L, seq, heads, hd = 2, 261, 8, 96
+    d = heads * hd
+    seq_pad = 384
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(L * seq, d, generator=g).cuda()
+    W = (torch.randn(3 * d, d, generator=g) * 0.04).cuda()
+    b = (torch.randn(3 * d, generator=g) * 0.05).cuda()
+    qw = (1 + 0.1 * torch.randn(hd, generator=g)).cuda()
+    kw = (1 + 0.1 * torch.randn(hd, generator=g)).cuda()
+    Q = torch.zeros(L * heads, seq_pad, hd, device="cuda")
+    K = torch.zeros_like(Q)
+    V = torch.zeros_like(Q)
+    scratch = torch.empty(L * seq, 3 * d, device="cuda")
+    _lib.check(lib.bd_qkv_project(_lib.ptr(x), _lib.ptr(W), _lib.ptr(b), _lib.ptr(qw), _lib.ptr(kw), _lib.ptr(Q), _lib.ptr(K),
+                                  _lib.ptr(V), _lib.ptr(scratch), L, seq, seq_pad, heads, hd, EX, sp()))
+    torch.cuda.synchronize()
+    qkv = F.linear(x.cpu(), W.cpu(), b.cpu()).view(L, seq, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    q = O.rms_norm(qkv[0], qw.cpu())
+    k = O.rms_norm(qkv[1], kw.cpu())
+    v = qkv[2]
+    for name, got, ref in (("Q", Q, q), ("K", K, k), ("V", V, v)):
+        ok, msg = report(name, got.view(L, heads, seq_pad, hd)[:, :, :seq], ref, tol_rel=5e-6)
+        assert ok, msg
+    Oo = torch.zeros(L * seq, d, device="cuda")
+    _lib.check(lib.bd_attention(_lib.ptr(Q), _lib.ptr(K), _lib.ptr(V), _lib.ptr(Oo), L, heads, hd, seq, seq_pad, hd ** -0.5, EX, 0, sp()))
+    torch.cuda.synchronize()
+    ref = F.scaled_dot_product_attention(q, k, v, scale=hd ** -0.5).transpose(1, 2).reshape(L * seq, d)
+    ok, msg = report("attention_f32", Oo, ref, tol_rel=5e-6)
+    assert ok, msg
+
+
+def test_corners_topk_matches_oracle(lib):
+    from oracle import boxdreamer_oracle as O
+    from boxdreamer_b200 import Engine
+    g = torch.Generator().manual_seed(11)
+    for S in (224, 336):
+        heat = torch.tanh(torch.randn(3, 8, S, S, generator=g))
+        # plant exact ties to exercise the lowest-index rule
+        heat[0, 0, 5, 7] = heat[0, 0, 100, 9] = heat[0, 0, 3, 200] = 0.999
+        idx_ref, kp_ref, nm_ref = O.corners_topk(heat)
+        hc = heat.cuda()
+        px = torch.empty(3, 8, 2, device="cuda")
+        nm = torch.empty(3, 8, 2, device="cuda")
+        idx = torch.empty(3, 8, 20, device="cuda", dtype=torch.int32)
+        _lib.check(lib.bd_corners_topk(None, _lib.ptr(hc), _lib.ptr(px), _lib.ptr(nm), _lib.ptr(idx), 3, S, sp()))
+        torch.cuda.synchronize()
+        assert torch.equal(idx.cpu().long(), idx_ref), "top-20 indices must be bit-exact (order included)"
+        assert torch.equal(px.cpu(), kp_ref)
+        assert torch.equal(nm.cpu(), nm_ref)
+
+
+def _rot_err_deg(Ra, Rb):
+    c = (np.trace(Ra.T @ Rb) - 1) / 2
+    return float(np.degrees(np.arccos(np.clip(c, -1, 1))))
+
+
+def test_pnp_matches_cv2_fixture(lib):
+    """Tolerance from BASELINE.json north_star: recovered R|t within 1e-3 deg (rotation), 1e-4 relative (translation).
+    At sigma=5 px a few near-planar cases are bistable: gate on pass-rate >= 95 %."""
+    import os
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "pnp_cv2.npz"))
+    for tag, min_rate in (("s0", 1.0), ("s2", 1.0), ("s5", 0.95)):
+        c2 = torch.from_numpy(fx[f"corners_{tag}"]).cuda()
+        X3 = torch.from_numpy(fx[f"bbox3d_{tag}"]).cuda()
+        Ks = torch.from_numpy(fx[f"K_{tag}"]).cuda()
+        n = c2.shape[0]
+        poses = torch.empty(n, 4, 4, device="cuda")
+        _lib.check(lib.bd_pnp(None, _lib.ptr(c2), _lib.ptr(X3), _lib.ptr(Ks), _lib.ptr(poses), None, n, 8, sp()))
+        torch.cuda.synchronize()
+        P = poses.cpu().numpy().astype(np.float64)
+        good = 0
+        worst = 0.0
+        for i in range(n):
+            re = _rot_err_deg(P[i, :3, :3], fx[f"R_{tag}"][i])
+            te = np.linalg.norm(P[i, :3, 3] - fx[f"t_{tag}"][i]) / np.linalg.norm(fx[f"t_{tag}"][i])
+            if re <= 1e-3 and te <= 1e-4:
+                good += 1
+            else:
+                worst = max(worst, re)
+            assert P[i, 3, 3] == 1.0
+        assert good / n >= min_rate, f"{tag}: {good}/{n} within tolerance, worst rot err {worst:.3e} deg"

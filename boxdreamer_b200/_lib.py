@@ -14,12 +14,13 @@ LIB_PATH = os.path.join(HERE, "libboxdreamer_b200.so")
 BD_F32, BD_BF16 = 0, 1
 PRECISION_EXACT, PRECISION_BF16 = 0, 1
 EPI_F32, EPI_GELU, EPI_RESID, EPI_QKV, EPI_ACT = 0, 1, 2, 3, 4
+PROF_CATS = ["gemm_qkv", "attention", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_other", "layernorm", "glue", "topk", "pnp"]
 
 # every symbol include/boxdreamer_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "bd_last_error", "bd_version", "bd_create", "bd_destroy", "bd_load_weight", "bd_finalize_weights",
     "bd_dino_forward", "bd_decoder_forward", "bd_corners_topk", "bd_pnp", "bd_forward", "bd_forward_host",
-    "bd_gemm", "bd_qkv_project", "bd_attention", "bd_layernorm",
+    "bd_gemm", "bd_qkv_project", "bd_attention", "bd_layernorm", "bd_launch_count", "bd_profile_enable", "bd_profile_read",
 ]
 
 
@@ -73,10 +74,14 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.bd_qkv_project.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.bd_attention.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, i32, vp]
     lib.bd_layernorm.argtypes = [vp, vp, vp, f32, vp, vp, i32, i32, vp]
+    lib.bd_launch_count.argtypes = [vp]
+    lib.bd_profile_enable.argtypes = [vp, i32]
+    lib.bd_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), i32]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("bd_last_error",):
+        if name not in ("bd_last_error", "bd_launch_count"):
             fn.restype = C.c_int
+    lib.bd_launch_count.restype = C.c_longlong
     _lib = lib
     return lib
 

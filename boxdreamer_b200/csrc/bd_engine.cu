@@ -67,7 +67,32 @@ struct bd_engine {
   void* in_images = nullptr; void* in_bbox = nullptr;  // device staging for bd_forward_host
   float* pos_dec = nullptr;  // f32 [P, d] 2-D sincos table
   cudaStream_t host_stream = nullptr;
+  // instrumentation: kernel launch counter and optional per-category CUDA-event timing
+  long long launches = 0;
+  bool profile = false;
+  struct Span { int cat; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> ev_pool;
+  double cat_ms[BD_PROF_NCAT] = {0};
+  long long cat_n[BD_PROF_NCAT] = {0};
 };
+
+static cudaEvent_t get_event(bd_engine* e) {
+  if (!e->ev_pool.empty()) { cudaEvent_t ev = e->ev_pool.back(); e->ev_pool.pop_back(); return ev; }
+  cudaEvent_t ev;
+  cudaEventCreate(&ev);
+  return ev;
+}
+
+// launches `expr` (a cudaError_t launcher that enqueues `nk` kernels) under category `cat`
+#define LAUNCH(cat, nk, expr)                                             \
+  do {                                                                    \
+    bd_engine::Span _sp{(cat), nullptr, nullptr};                         \
+    if (e->profile) { _sp.a = get_event(e); cudaEventRecord(_sp.a, s); }  \
+    CK(expr);                                                             \
+    e->launches += (nk);                                                  \
+    if (e->profile) { _sp.b = get_event(e); cudaEventRecord(_sp.b, s); e->spans.push_back(_sp); } \
+  } while (0)
 
 static size_t act_size(const bd_engine* e) { return e->tc ? 2 : 4; }
 
@@ -336,25 +361,25 @@ static cudaError_t ln_act(bd_engine* e, const float* x, const float* w, const fl
 static int run_block(bd_engine* e, float* X, const std::string& p, int L, int seq, int seq_pad, int heads, int hd, float ln_eps,
                      bool qk_norm, const char* g1, const char* g2, cudaStream_t s) {
   const int M = L * seq, d = e->d;
-  CK(ln_act(e, X, WF(e, p + "norm1.weight"), WF(e, p + "norm1.bias"), ln_eps, M, s));
+  LAUNCH(BD_PROF_LAYERNORM, 1, ln_act(e, X, WF(e, p + "norm1.weight"), WF(e, p + "norm1.bias"), ln_eps, M, s));
   GemmEpi q;
   q.bias = WF(e, p + "attn.qkv.bias");
   q.q = e->Q; q.k = e->K; q.v = e->V;
   q.q_norm_w = qk_norm ? WF(e, p + "attn.q_norm.weight") : nullptr;
   q.k_norm_w = qk_norm ? WF(e, p + "attn.k_norm.weight") : nullptr;
   q.seq = seq; q.seq_pad = seq_pad; q.heads = heads; q.head_dim = hd; q.rms_eps = 1e-6f;
-  CK(linear(e, e->H, p + "attn.qkv.weight", M, 3 * d, d, EPI_QKV, q, s));
-  CK(attention(e, L, heads, hd, seq, seq_pad, s));
+  LAUNCH(BD_PROF_GEMM_QKV, e->tc ? 1 : 2, linear(e, e->H, p + "attn.qkv.weight", M, 3 * d, d, EPI_QKV, q, s));
+  LAUNCH(BD_PROF_ATTENTION, 1, attention(e, L, heads, hd, seq, seq_pad, s));
   GemmEpi pr;
   pr.bias = WF(e, p + "attn.proj.bias"); pr.out_f32 = X; pr.ldo = d; pr.gamma = g1 ? WF(e, p + g1) : nullptr;
-  CK(linear(e, e->O, p + "attn.proj.weight", M, d, d, EPI_RESID, pr, s));
-  CK(ln_act(e, X, WF(e, p + "norm2.weight"), WF(e, p + "norm2.bias"), ln_eps, M, s));
+  LAUNCH(BD_PROF_GEMM_PROJ, 1, linear(e, e->O, p + "attn.proj.weight", M, d, d, EPI_RESID, pr, s));
+  LAUNCH(BD_PROF_LAYERNORM, 1, ln_act(e, X, WF(e, p + "norm2.weight"), WF(e, p + "norm2.bias"), ln_eps, M, s));
   GemmEpi f1;
   f1.bias = WF(e, p + "mlp.fc1.bias"); f1.out_act = e->G;
-  CK(linear(e, e->H, p + "mlp.fc1.weight", M, 4 * d, d, EPI_GELU, f1, s));
+  LAUNCH(BD_PROF_GEMM_FC1, 1, linear(e, e->H, p + "mlp.fc1.weight", M, 4 * d, d, EPI_GELU, f1, s));
   GemmEpi f2;
   f2.bias = WF(e, p + "mlp.fc2.bias"); f2.out_f32 = X; f2.ldo = d; f2.gamma = g2 ? WF(e, p + g2) : nullptr;
-  CK(linear(e, e->G, p + "mlp.fc2.weight", M, d, 4 * d, EPI_RESID, f2, s));
+  LAUNCH(BD_PROF_GEMM_FC2, 1, linear(e, e->G, p + "mlp.fc2.weight", M, d, 4 * d, EPI_RESID, f2, s));
   return BD_OK;
 }
 
@@ -362,23 +387,24 @@ static int dino_forward_impl(bd_engine* e, const void* images, int dtype, float*
   if (!e->finalized) return fail(BD_ERR_STATE, "weights not finalised (call bd_finalize_weights)");
   if (L <= 0 || L > e->Lmax) return fail(BD_ERR_INVALID, "bd_dino_forward: L exceeds max_batch*max_views");
   const int P = e->P, d = e->d;
-  CK(im2col_patches(images, dtype == BD_BF16, e->A_pe, e->tc, L, e->S, e->patch, e->kpe, s));
+  LAUNCH(BD_PROF_GLUE, 1, im2col_patches(images, dtype == BD_BF16, e->A_pe, e->tc, L, e->S, e->patch, e->kpe, s));
   GemmEpi pe;
   pe.bias = WF(e, "dino.patch_embed.proj.bias");
   pe.out_f32 = e->X_dino; pe.ldo = d;
   pe.rp_in = P; pe.rp_out = e->n_tok; pe.rp_off = e->n_prefix;
   pe.addtab = WF(e, "dino.pos_embed") + d;  // rows 1.. of the (already interpolated) table
-  CK(linear(e, e->A_pe, "dino.patch_embed.proj.weight", L * P, d, e->kpe, EPI_F32, pe, s));
-  CK(dino_prefix_tokens(e->X_dino, WF(e, "dino.cls_token"), WF(e, "dino.pos_embed"), WF(e, "dino.register_tokens"), L, e->n_tok,
-                        e->cfg.dino_registers, d, s));
+  LAUNCH(BD_PROF_GEMM_OTHER, 1, linear(e, e->A_pe, "dino.patch_embed.proj.weight", L * P, d, e->kpe, EPI_F32, pe, s));
+  LAUNCH(BD_PROF_GLUE, 1, dino_prefix_tokens(e->X_dino, WF(e, "dino.cls_token"), WF(e, "dino.pos_embed"),
+                                             WF(e, "dino.register_tokens"), L, e->n_tok, e->cfg.dino_registers, d, s));
   for (int i = 0; i < e->cfg.dino_layers; ++i) {
     int r = run_block(e, e->X_dino, "dino.blocks." + std::to_string(i) + ".", L, e->n_tok, e->seqpad_dino, e->cfg.dino_heads,
                       e->hd_dino, 1e-6f, false, "ls1.gamma", "ls2.gamma", s);
     if (r != BD_OK) return r;
   }
   // final LayerNorm, patch tokens only (vision_transformer.py:263-267)
-  CK(layernorm(e->X_dino, WF(e, "dino.norm.weight"), WF(e, "dino.norm.bias"), 1e-6f, feats_out,
-               e->tc ? reinterpret_cast<bf16*>(e->feats_act) : nullptr, L * P, d, P, e->n_tok, e->n_prefix, s));
+  LAUNCH(BD_PROF_LAYERNORM, 1, layernorm(e->X_dino, WF(e, "dino.norm.weight"), WF(e, "dino.norm.bias"), 1e-6f, feats_out,
+                                         e->tc ? reinterpret_cast<bf16*>(e->feats_act) : nullptr, L * P, d, P, e->n_tok,
+                                         e->n_prefix, s));
   return BD_OK;
 }
 
@@ -390,35 +416,35 @@ static int decoder_forward_impl(bd_engine* e, const void* bbox_feat, int dtype, 
   const int pp8 = e->patch * e->patch * 8;
   const void* fin = feats;
   if (e->tc) {
-    if (!feats_act_valid) CK(cast_f32_to_bf16(feats, reinterpret_cast<bf16*>(e->feats_act), static_cast<size_t>(M) * d, s));
+    if (!feats_act_valid) LAUNCH(BD_PROF_GLUE, 1, cast_f32_to_bf16(feats, reinterpret_cast<bf16*>(e->feats_act), static_cast<size_t>(M) * d, s));
     fin = e->feats_act;
   }
   // rgb branch: input_transform Mlp -> (LayerNorm without affine happens inside the fusion kernel)
   GemmEpi t1;
   t1.bias = WF(e, "decoder.input_transform.fc1.bias"); t1.out_act = e->G;
-  CK(linear(e, fin, "decoder.input_transform.fc1.weight", M, d, d, EPI_GELU, t1, s));
+  LAUNCH(BD_PROF_GEMM_OTHER, 1, linear(e, fin, "decoder.input_transform.fc1.weight", M, d, d, EPI_GELU, t1, s));
   GemmEpi t2;
   t2.bias = WF(e, "decoder.input_transform.fc2.bias"); t2.out_f32 = e->R; t2.ldo = d;
-  CK(linear(e, e->G, "decoder.input_transform.fc2.weight", M, d, d, EPI_F32, t2, s));
+  LAUNCH(BD_PROF_GEMM_OTHER, 1, linear(e, e->G, "decoder.input_transform.fc2.weight", M, d, d, EPI_F32, t2, s));
   // pose branch: patchify(bbox_feat) -> bbox_emb
-  CK(patchify_heat(bbox_feat, dtype == BD_BF16, e->A_bb, e->tc, L, 8, e->S, e->patch, s));
+  LAUNCH(BD_PROF_GLUE, 1, patchify_heat(bbox_feat, dtype == BD_BF16, e->A_bb, e->tc, L, 8, e->S, e->patch, s));
   GemmEpi be;
   be.bias = WF(e, "decoder.bbox_emb.bias"); be.out_f32 = e->PF; be.ldo = d;
-  CK(linear(e, e->A_bb, "decoder.bbox_emb.weight", M, d, pp8, EPI_F32, be, s));
-  CK(betr_fuse(e->PF, e->R, WF(e, "decoder.bbox_learnable_query"), e->pos_dec, query_idx, e->X_dec, B, T, P, d, 1e-6f, s));
+  LAUNCH(BD_PROF_GEMM_OTHER, 1, linear(e, e->A_bb, "decoder.bbox_emb.weight", M, d, pp8, EPI_F32, be, s));
+  LAUNCH(BD_PROF_GLUE, 1, betr_fuse(e->PF, e->R, WF(e, "decoder.bbox_learnable_query"), e->pos_dec, query_idx, e->X_dec, B, T, P, d, 1e-6f, s));
   const int seq = T * P, seq_pad = (seq + 127) / 128 * 128;
   for (int i = 0; i < e->cfg.dec_layers; ++i) {
     int r = run_block(e, e->X_dec, "decoder.attn." + std::to_string(i) + ".", B, seq, seq_pad, e->cfg.dec_heads, e->hd_dec, 1e-5f,
                       true, nullptr, nullptr, s);
     if (r != BD_OK) return r;
   }
-  CK(gather_query(e->X_dec, query_idx, e->tc ? nullptr : reinterpret_cast<float*>(e->Xq),
-                  e->tc ? reinterpret_cast<bf16*>(e->Xq) : nullptr, B, T, P, d, s));
+  LAUNCH(BD_PROF_GLUE, 1, gather_query(e->X_dec, query_idx, e->tc ? nullptr : reinterpret_cast<float*>(e->Xq),
+                                       e->tc ? reinterpret_cast<bf16*>(e->Xq) : nullptr, B, T, P, d, s));
   float* lg = logits_out ? logits_out : e->logits;
   GemmEpi bp;
   bp.bias = WF(e, "decoder.bbox_proj.bias"); bp.out_f32 = lg; bp.ldo = pp8;
-  CK(linear(e, e->Xq, "decoder.bbox_proj.weight", B * P, pp8, d, EPI_F32, bp, s));
-  CK(unpatchify_sigmoid(lg, heat_out, B, 8, e->S, e->patch, s));
+  LAUNCH(BD_PROF_GEMM_OTHER, 1, linear(e, e->Xq, "decoder.bbox_proj.weight", B * P, pp8, d, EPI_F32, bp, s));
+  LAUNCH(BD_PROF_GLUE, 1, unpatchify_sigmoid(lg, heat_out, B, 8, e->S, e->patch, s));
   return BD_OK;
 }
 
@@ -472,10 +498,10 @@ extern "C" int bd_forward(bd_handle e, const void* images, const void* bbox_feat
   if (r != BD_OK) return r;
   r = decoder_forward_impl(e, bbox_feat, in_dtype, e->feats, e->tc, query_idx, heat, nullptr, B, T, s);
   if (r != BD_OK) return r;
-  CK(corners_topk(heat, corners_px, corners_norm, nullptr, B, 8, e->S, s));
-  cudaError_t ce = pnp_solve(corners_px, bbox3d_q, K_q, poses_out, to_opts(opts), B, 8, s);
-  if (ce == cudaErrorNotSupported) return fail(BD_ERR_UNSUPPORTED, "bd_forward: pnp mode not built");
-  CK(ce);
+  LAUNCH(BD_PROF_TOPK, 1, corners_topk(heat, corners_px, corners_norm, nullptr, B, 8, e->S, s));
+  const PnpOpts po = to_opts(opts);
+  if (po.mode != 0 && po.mode != 1) return fail(BD_ERR_UNSUPPORTED, "bd_forward: pnp mode not built");
+  LAUNCH(BD_PROF_PNP, 1, pnp_solve(corners_px, bbox3d_q, K_q, poses_out, po, B, 8, s));
   return BD_OK;
 }
 
@@ -569,5 +595,34 @@ extern "C" int bd_layernorm(const float* x, const float* w, const float* b, floa
                             int32_t d, void* stream) {
   if (!x || (!out_f32 && !out_bf16)) return fail(BD_ERR_INVALID, "bd_layernorm: null argument");
   CK(layernorm(x, w, b, eps, out_f32, reinterpret_cast<bf16*>(out_bf16), rows, d, 0, 0, 0, reinterpret_cast<cudaStream_t>(stream)));
+  return BD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// instrumentation
+
+extern "C" long long bd_launch_count(bd_handle e) { return e ? e->launches : 0; }
+
+extern "C" int bd_profile_enable(bd_handle e, int32_t on) {
+  if (!e) return fail(BD_ERR_INVALID, "bd_profile_enable: null handle");
+  e->profile = on != 0;
+  return BD_OK;
+}
+
+extern "C" int bd_profile_read(bd_handle e, double* ms_out, int64_t* count_out, int32_t reset) {
+  if (!e || !ms_out || !count_out) return fail(BD_ERR_INVALID, "bd_profile_read: null argument");
+  CK(cudaDeviceSynchronize());
+  for (auto& sp : e->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+      e->cat_ms[sp.cat] += ms;
+      e->cat_n[sp.cat] += 1;
+    }
+    e->ev_pool.push_back(sp.a);
+    e->ev_pool.push_back(sp.b);
+  }
+  e->spans.clear();
+  for (int i = 0; i < BD_PROF_NCAT; ++i) { ms_out[i] = e->cat_ms[i]; count_out[i] = e->cat_n[i]; }
+  if (reset) for (int i = 0; i < BD_PROF_NCAT; ++i) { e->cat_ms[i] = 0; e->cat_n[i] = 0; }
   return BD_OK;
 }

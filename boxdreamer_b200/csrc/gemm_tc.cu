@@ -30,7 +30,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NSTAGE = (BN == 256) ? 4 : 5;
+  static constexpr int NSTAGE = 4;
   static constexpr int STAGING_BYTES = N_EPI_WARPS * 32 * 32 * 4;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment

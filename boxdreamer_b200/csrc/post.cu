@@ -94,51 +94,58 @@ cudaError_t corners_topk(const float* heat, float* corners_px, float* corners_no
 // reprojection error over all points, run to convergence, all in fp64.  One thread per query.
 
 static constexpr int PNP_MAXPTS = 16;
+#define BD_HD __host__ __device__
 
-__device__ void jacobi_eig_sym12(double (&A)[12][12], double (&V)[12][12]) {
-  for (int i = 0; i < 12; ++i)
-    for (int j = 0; j < 12; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+// Cyclic Jacobi on a symmetric 12x12 (row-major, flat).  NOTE: written with flat indexing and non-unrolled inner
+// loops on purpose -- nvcc 12.9 miscompiles the fully unrolled two-pass update on a `double (&)[12][12]` for sm_100a
+// (host and device results diverge; scripts/jacobi_variants.cu reproduces it), the flat form is exact.
+BD_HD void jacobi_eig_sym12(double* A, double* V) {
+  for (int i = 0; i < 144; ++i) V[i] = 0.0;
+  for (int i = 0; i < 12; ++i) V[i * 13] = 1.0;
   for (int sweep = 0; sweep < 40; ++sweep) {
     double off = 0.0, dg = 0.0;
     for (int i = 0; i < 12; ++i) {
-      dg += A[i][i] * A[i][i];
-      for (int j = i + 1; j < 12; ++j) off += A[i][j] * A[i][j];
+      dg += A[i * 13] * A[i * 13];
+      for (int j = i + 1; j < 12; ++j) off += A[i * 12 + j] * A[i * 12 + j];
     }
     if (off <= 1e-60 * dg || off == 0.0) break;
     for (int p = 0; p < 11; ++p) {
       for (int q = p + 1; q < 12; ++q) {
-        const double apq = A[p][q];
+        const double apq = A[p * 12 + q];
         if (apq == 0.0) continue;
-        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        const double theta = (A[q * 13] - A[p * 13]) / (2.0 * apq);
         const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
         const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll 1
         for (int k = 0; k < 12; ++k) {
-          const double akp = A[k][p], akq = A[k][q];
-          A[k][p] = c * akp - s * akq;
-          A[k][q] = s * akp + c * akq;
+          const double akp = A[k * 12 + p], akq = A[k * 12 + q];
+          A[k * 12 + p] = c * akp - s * akq;
+          A[k * 12 + q] = s * akp + c * akq;
         }
+#pragma unroll 1
         for (int k = 0; k < 12; ++k) {
-          const double apk = A[p][k], aqk = A[q][k];
-          A[p][k] = c * apk - s * aqk;
-          A[q][k] = s * apk + c * aqk;
+          const double apk = A[p * 12 + k], aqk = A[q * 12 + k];
+          A[p * 12 + k] = c * apk - s * aqk;
+          A[q * 12 + k] = s * apk + c * aqk;
         }
+#pragma unroll 1
         for (int k = 0; k < 12; ++k) {
-          const double vkp = V[k][p], vkq = V[k][q];
-          V[k][p] = c * vkp - s * vkq;
-          V[k][q] = s * vkp + c * vkq;
+          const double vkp = V[k * 12 + p], vkq = V[k * 12 + q];
+          V[k * 12 + p] = c * vkp - s * vkq;
+          V[k * 12 + q] = s * vkp + c * vkq;
         }
       }
     }
   }
 }
 
-__device__ __forceinline__ double det3(const double (&R)[3][3]) {
+BD_HD __forceinline__ double det3(const double (&R)[3][3]) {
   return R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
          R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
 }
 
 // orthogonal polar factor by Newton iteration R <- (R + R^-T)/2
-__device__ void nearest_rotation(double (&R)[3][3], int iters) {
+BD_HD void nearest_rotation(double (&R)[3][3], int iters) {
   for (int it = 0; it < iters; ++it) {
     const double d = det3(R);
     if (fabs(d) < 1e-300) return;
@@ -163,7 +170,7 @@ __device__ void nearest_rotation(double (&R)[3][3], int iters) {
   }
 }
 
-__device__ void rodrigues_exp(const double (&w)[3], double (&E)[3][3]) {
+BD_HD void rodrigues_exp(const double (&w)[3], double (&E)[3][3]) {
   const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
   const double th = sqrt(th2);
   double a, b;  // E = I + a K + b K^2
@@ -179,7 +186,7 @@ __device__ void rodrigues_exp(const double (&w)[3], double (&E)[3][3]) {
 }
 
 // solve (H + lam*diag(H)) x = -g by Gaussian elimination with partial pivoting; false if singular
-__device__ bool solve6(const double (&H)[6][6], const double (&g)[6], double lam, double (&x)[6]) {
+BD_HD bool solve6(const double (&H)[6][6], const double (&g)[6], double lam, double (&x)[6]) {
   double M[6][7];
   for (int i = 0; i < 6; ++i) {
     for (int j = 0; j < 6; ++j) M[i][j] = H[i][j] + (i == j ? lam * H[i][i] : 0.0);
@@ -213,7 +220,7 @@ struct PnpProblem {
   int n;
 };
 
-__device__ double reproj_cost(const PnpProblem& pb, const double (&R)[3][3], const double (&t)[3], double (*res)[2],
+BD_HD double reproj_cost(const PnpProblem& pb, const double (&R)[3][3], const double (&t)[3], double (*res)[2],
                               double (*Xc)[3]) {
   double cost = 0.0;
   for (int i = 0; i < pb.n; ++i) {
@@ -228,10 +235,9 @@ __device__ double reproj_cost(const PnpProblem& pb, const double (&R)[3][3], con
   return cost;
 }
 
-__device__ void pnp_dlt_init(const PnpProblem& pb, double (&R)[3][3], double (&t)[3]) {
-  double A[12][12], V[12][12];
-  for (int i = 0; i < 12; ++i)
-    for (int j = 0; j < 12; ++j) A[i][j] = 0.0;
+BD_HD void pnp_dlt_init(const PnpProblem& pb, double (&R)[3][3], double (&t)[3]) {
+  double A[144], V[144];
+  for (int i = 0; i < 144; ++i) A[i] = 0.0;
   for (int i = 0; i < pb.n; ++i) {
     const double xn = (pb.uv[i][0] - pb.cx) / pb.fx, yn = (pb.uv[i][1] - pb.cy) / pb.fy;
     double r1[12], r2[12];
@@ -242,16 +248,16 @@ __device__ void pnp_dlt_init(const PnpProblem& pb, double (&R)[3][3], double (&t
     }
     r1[3] = 1.0; r2[7] = 1.0; r1[11] = -xn; r2[11] = -yn;
     for (int a = 0; a < 12; ++a)
-      for (int b = 0; b < 12; ++b) A[a][b] += r1[a] * r1[b] + r2[a] * r2[b];
+      for (int b = 0; b < 12; ++b) A[a * 12 + b] += r1[a] * r1[b] + r2[a] * r2[b];
   }
   jacobi_eig_sym12(A, V);
   int kmin = 0;
   for (int k = 1; k < 12; ++k)
-    if (A[k][k] < A[kmin][kmin]) kmin = k;
+    if (A[k * 13] < A[kmin * 13]) kmin = k;
   double Rd[3][3], td[3];
   for (int a = 0; a < 3; ++a) {
-    for (int b = 0; b < 3; ++b) Rd[a][b] = V[a * 4 + b][kmin];
-    td[a] = V[a * 4 + 3][kmin];
+    for (int b = 0; b < 3; ++b) Rd[a][b] = V[(a * 4 + b) * 12 + kmin];
+    td[a] = V[(a * 4 + 3) * 12 + kmin];
   }
   if (det3(Rd) < 0.0) {
     for (int a = 0; a < 3; ++a) {
@@ -271,7 +277,7 @@ __device__ void pnp_dlt_init(const PnpProblem& pb, double (&R)[3][3], double (&t
   nearest_rotation(R, 60);
 }
 
-__device__ void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int max_iter) {
+BD_HD void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int max_iter) {
   double res[PNP_MAXPTS][2], Xc[PNP_MAXPTS][3];
   double lam = 1e-3;
   double cost = reproj_cost(pb, R, t, res, Xc);

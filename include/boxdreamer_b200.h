@@ -136,6 +136,18 @@ int bd_attention(const void* Q, const void* K, const void* V, void* O, int32_t L
 int bd_layernorm(const float* x, const float* w, const float* b, float eps, float* out_f32, void* out_bf16, int32_t rows,
                  int32_t d, void* stream);
 
+/* ---- instrumentation (bench.py: gpu_launches and the in-step roofline timing) ---- */
+enum {
+  BD_PROF_GEMM_QKV = 0, BD_PROF_ATTENTION = 1, BD_PROF_GEMM_PROJ = 2, BD_PROF_GEMM_FC1 = 3, BD_PROF_GEMM_FC2 = 4,
+  BD_PROF_GEMM_OTHER = 5, BD_PROF_LAYERNORM = 6, BD_PROF_GLUE = 7, BD_PROF_TOPK = 8, BD_PROF_PNP = 9, BD_PROF_NCAT = 10
+};
+/* kernels this handle has launched so far */
+long long bd_launch_count(bd_handle h);
+/* when on, every kernel launch is bracketed by CUDA events on its stream */
+int bd_profile_enable(bd_handle h, int32_t on);
+/* synchronises, then returns accumulated milliseconds and launch counts per BD_PROF_* category */
+int bd_profile_read(bd_handle h, double* ms_out, int64_t* count_out, int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif

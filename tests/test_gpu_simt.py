@@ -21,15 +21,15 @@ def test_gemm_f32_plain(lib, M, N, K):
     b = torch.randn(N, generator=g).cuda()
     ref = (A.double() @ W.double().t() + b.double()).float()
     out = gemm(A, W, b, M, N, K, _lib.EPI_F32, EX)
-    ok, msg = report("gemm_f32", out, ref, tol_rel=2e-6)
+    ok, msg = report("gemm_f32", out, ref, tol_rel=5e-6)
     assert ok, msg
     out = gemm(A, W, b, M, N, K, _lib.EPI_GELU, EX)
-    ok, msg = report("gemm_f32_gelu", out, F.gelu(ref), tol_rel=3e-6)
+    ok, msg = report("gemm_f32_gelu", out, F.gelu(ref), tol_rel=6e-6)
     assert ok, msg
     res0 = torch.randn(M, N, generator=g).cuda()
     gam = torch.randn(N, generator=g).cuda()
     out = gemm(A, W, b, M, N, K, _lib.EPI_RESID, EX, gamma=gam, out=res0.clone())
-    ok, msg = report("gemm_f32_resid", out, res0 + gam * ref, tol_rel=3e-6)
+    ok, msg = report("gemm_f32_resid", out, res0 + gam * ref, tol_rel=6e-6)
     assert ok, msg
 
 

@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the BoxDreamer inference hot path (BASELINE.json: queries/sec, 224 px, 5 references).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One step = one pass of the whole path (DINOv2 -> BETR -> heat maps -> top-20 corners -> PnP) over one batch of
+synthetic queries; the N=1 workload is BASELINE.json configs[1]: batch 64 queries x 5 reference views (T = 6),
+224 px, bf16.  Weak scaling: every rank processes its own 64-query shard (configs[2] at N = 8), weights arrive by one
+broadcast from rank 0, packed poses + corners are all-gathered every step (inside the timed region).
+
+Printed JSON (one line, rank 0): see the contract in the task statement; extra keys `roofline` (attention kernel,
+in-step CUDA-event timing on the launching stream), `cpu_baseline` (the CPU oracle port on this box's host cores),
+`e2e` (C-ABI call with HOST buffers, H2D/D2H inside the timed region), `gpu_launches`, `clocks`, `kernel_ms`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "queries_per_sec"
+UNIT = "queries/s"
+B_PER_GPU, T_VIEWS, IMG = 64, 6, 224
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_tflops": d.get("bf16_tflops"), "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+def flops_per_query(T=T_VIEWS, P=256, d=768, dec_layers=12, dino_layers=12, n_tok=261):
+    """Algorithmic FLOPs (2 x MACs), BASELINE.md section 3."""
+    N = T * P
+    dino_lin = dino_layers * (2 * n_tok * d * (3 * d + d + 4 * d + 4 * d)) + 2 * P * 588 * d
+    dino_att = dino_layers * 4 * n_tok * n_tok * d
+    dino = T * (dino_lin + dino_att)
+    betr_lin = dec_layers * 2 * N * d * (12 * d)
+    betr_att = dec_layers * 4 * N * N * d
+    fusion = 2 * N * d * (2 * d) + 2 * N * 1568 * d
+    head = 2 * P * d * 1568
+    return {"dino": dino, "betr_linear": betr_lin, "betr_attention": betr_att, "fusion_head": fusion + head,
+            "total": dino + betr_lin + betr_att + fusion + head}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+            clocks, powers, reasons = [], [], set()
+            for r in rows:
+                r = [x.strip() for x in r]
+                if len(r) < 9:
+                    continue
+                try:
+                    clocks.append(float(r[1]))
+                    out["sm_max_mhz"] = float(r[2])
+                    powers.append(float(r[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            if clocks:
+                # median over the samples taken under load (power above half of the max seen)
+                pmax = max(powers) if powers else 0
+                loaded = sorted(c for c, p in zip(clocks, powers) if p >= 0.5 * pmax) or sorted(clocks)
+                out["sm_mhz"] = loaded[len(loaded) // 2]
+                out["power_w_max"] = pmax
+            out["reasons"] = sorted(reasons)
+            out["samples"] = len(clocks)
+        except Exception:
+            pass
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement of the reference's own path (oracle port), all host threads
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    from boxdreamer_b200 import synth
+    from oracle import boxdreamer_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dec, dino = synth.synth_decoder_state_dict(0), synth.synth_dino_state_dict(0)
+    data1 = synth.synth_inputs(1, T_VIEWS, IMG, seed=1235)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.forward(data1, dec, dino)
+        t_query = time.perf_counter() - t0
+    budget = 150.0
+    q = max(1, min(8, int(budget / max(t_query, 1e-3) / max(args.steps + args.warmup, 1))))
+    data = synth.synth_inputs(q, T_VIEWS, IMG, seed=1235)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.forward(data, dec, dino)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.forward(data, dec, dino)
+        dt = time.perf_counter() - t0
+    value = q * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"batch={B_PER_GPU} queries x {T_VIEWS - 1} refs, {IMG}px (configs[1]); each step = a {q}-query sample",
+                   "sample_queries_per_step": q, "views": T_VIEWS},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{q} queries/step x {args.steps} steps, torch fp32 CPU restatement of BoxDreamer.forward (oracle/), numpy PnP"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+
+
+def cpu_baseline_sample():
+    """Bounded CPU sample on rank 0 (N=1 only): the oracle port on all host cores."""
+    from boxdreamer_b200 import synth
+    from oracle import boxdreamer_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dec, dino = synth.synth_decoder_state_dict(0), synth.synth_dino_state_dict(0)
+    data = synth.synth_inputs(2, T_VIEWS, IMG, seed=1235)
+    with torch.no_grad():
+        O.forward(synth.synth_inputs(1, T_VIEWS, IMG, seed=1), dec, dino)  # warm-up
+        n, t0 = 0, time.perf_counter()
+        while True:
+            O.forward(data, dec, dino)
+            n += 2
+            if time.perf_counter() - t0 > 12.0:
+                break
+        dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} queries (B=2 x T={T_VIEWS} per call) in {dt:.1f} s, torch fp32 CPU restatement (oracle/) + numpy PnP"}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from boxdreamer_b200 import _lib, synth
+    from boxdreamer_b200 import dist as bdist
+    from boxdreamer_b200.model import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B, T, S = B_PER_GPU, T_VIEWS, IMG
+    peaks = load_peaks()
+
+    # ---- weights: rank 0 synthesises, one NCCL broadcast each for decoder and DINOv2 ----
+    dec_shapes, dino_shapes = synth.decoder_param_shapes(), synth.dino_param_shapes()
+    if world > 1:
+        dec = bdist.broadcast_state(synth.synth_decoder_state_dict(0) if rank == 0 else None, dec_shapes, 0, dev)
+        dino = bdist.broadcast_state(synth.synth_dino_state_dict(0) if rank == 0 else None, dino_shapes, 0, dev)
+    else:
+        dec, dino = synth.synth_decoder_state_dict(0), synth.synth_dino_state_dict(0)
+
+    from boxdreamer_b200.config import make_config
+    from boxdreamer_b200 import BoxDreamer
+    model = BoxDreamer(make_config(S), precision="bf16")
+    model.load_state_dict({k: v.cpu() for k, v in dec.items()}, strict=True)
+    model.rgb_encoder.model.load_state_dict({k: v.cpu() for k, v in dino.items()}, strict=True)
+    model = model.to(dev).eval()
+
+    # ---- inputs: this rank's shard of the global batch, bf16, pinned on the host ----
+    data = synth.synth_inputs(B, T, S, seed=1235 + rank, dtype=torch.bfloat16)
+    mask = torch.zeros(B, T, dtype=torch.bool)
+    mask[torch.arange(B), data["query_idx"]] = True
+    h_images = data["images"].contiguous().pin_memory()
+    h_bbox = data["bbox_feat"].contiguous().pin_memory()
+    h_qidx = data["query_idx"].contiguous().pin_memory()
+    h_K = data["non_ndc_intrinsics"][mask].float().contiguous().pin_memory()
+    h_X = data["bbox_3d"][mask].float().contiguous().pin_memory()
+    d_images, d_bbox, d_qidx = h_images.to(dev), h_bbox.to(dev), h_qidx.to(dev)
+    d_K, d_X = h_K.to(dev), h_X.to(dev)
+    h2d = sum(t.numel() * t.element_size() for t in (h_images, h_bbox, h_qidx, h_K, h_X))
+    d2h = B * (16 + 16 + 16) * 4
+
+    eng = model._engine_for(d_images, B, T)
+    lib = eng.lib
+    counts = [B] * world
+
+    def step():
+        heat, px, nm, poses = eng.forward(d_images, d_bbox, d_qidx, d_X, d_K, want_heat=False)
+        if world > 1:
+            return bdist.all_gather_results(bdist.pack_results(poses, nm), counts)
+        return poses
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: K steps, CUDA events, clocks sampled during it ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = lib.bd_launch_count(eng.handle)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.bd_launch_count(eng.handle) - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- in-step per-kernel timing (CUDA events on the launching stream, same workload) ----
+    import ctypes as C
+    _lib.check(lib.bd_profile_enable(eng.handle, 1))
+    ms_arr, n_arr = (C.c_double * 10)(), (C.c_int64 * 10)()
+    _lib.check(lib.bd_profile_read(eng.handle, ms_arr, n_arr, 1))
+    prof_steps = min(args.steps, 3)
+    for _ in range(prof_steps):
+        eng.forward(d_images, d_bbox, d_qidx, d_X, d_K, want_heat=False)
+    _lib.check(lib.bd_profile_read(eng.handle, ms_arr, n_arr, 1))
+    _lib.check(lib.bd_profile_enable(eng.handle, 0))
+    kernel_ms = {name: (ms_arr[i] / prof_steps) for i, name in enumerate(_lib.PROF_CATS)}
+    kernel_n = {name: int(n_arr[i] // prof_steps) for i, name in enumerate(_lib.PROF_CATS)}
+
+    # roofline of the attention kernel (north_star): QK^T and PV FLOPs only, 4*N^2*d per (sample, layer)
+    fl = flops_per_query()
+    att_flops_step = B * (fl["betr_attention"] + T * 12 * 4 * 261 * 261 * 768)
+    att_launches = max(kernel_n["attention"], 1)
+    att_ms = kernel_ms["attention"]
+    peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+    achieved = att_flops_step / (att_ms / 1e3) / 1e12 if att_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "attn_tc_kernel (decoder 8x96 N=1536 + DINOv2 12x64 N=261)", "achieved": achieved,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
+                "flops_per_launch": att_flops_step / att_launches, "ms_per_launch": att_ms / att_launches,
+                "launches_per_step": att_launches}
+    gemm_ms = sum(kernel_ms[k] for k in ("gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_other"))
+    gemm_flops_step = B * (fl["total"] - fl["betr_attention"]) - B * T * 12 * 4 * 261 * 261 * 768
+    roofline_gemm = {"bound": "tensor", "achieved": gemm_flops_step / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0, "peak": peak,
+                     "unit": "TFLOP/s"}
+    roofline_gemm["frac"] = roofline_gemm["achieved"] / peak if peak else None
+    roofline_e2e = {"achieved": fl["total"] * value / world / 1e12, "peak": peak, "unit": "TFLOP/s"}
+    roofline_e2e["frac"] = roofline_e2e["achieved"] / peak if peak else None
+
+    # ---- e2e: C-ABI call with HOST buffers (pinned), H2D + D2H inside the timed region ----
+    e2e_value, e2e_steps = None, 0
+    if not args.quick:
+        for _ in range(2):
+            eng.forward_host(h_images, h_bbox, h_qidx, h_X, h_K)
+        barrier()
+        e2e_steps = max(2, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.forward_host(h_images, h_bbox, h_qidx, h_X, h_K)  # synchronises on return
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_value = world * B * e2e_steps / float(te.item())
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
+        cpu_base = cpu_baseline_sample()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"batch={B} queries x {T - 1} reference views per GPU, {S}px, bf16 (BASELINE configs[1]; configs[2] at 8 GPUs)",
+                       "global_batch": world * B, "views": T, "img_size": S, "weights": "random-init (synth seed 0)",
+                       "l2": "inputs (424 MB/step) exceed L2; no flush needed", "parallelism": f"query-shard x{world}",
+                       "attn_variant": int(eng.cfg.attn_variant)},
+            "roofline": roofline, "roofline_gemm": roofline_gemm, "roofline_e2e": roofline_e2e,
+            "cpu_baseline": cpu_base,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "bd_forward_host (C ABI, pinned host buffers)", "steps": e2e_steps},
+            "gpu_launches": int(launches), "kernel_ms_per_step": kernel_ms, "kernel_launches_per_step": kernel_n,
+            "clocks": clocks, "flops_per_query": fl["total"],
+        }
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="timed loop only (for runs under ncu): no e2e / cpu_baseline legs")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        return run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    sys.exit(main())

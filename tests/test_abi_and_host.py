@@ -33,14 +33,14 @@ def test_no_cpu_fallback(lib):
     cfg = _lib.BdConfig(224, 14, 768, 12, 8, 12, 12, 4, 37, 0, 1, 1, 2)
     rc = lib.bd_create(C.byref(h), C.byref(cfg))
     assert rc == -2 and b"no CUDA device" in lib.bd_last_error()
-    from oracle.ref_import import make_config
+    from boxdreamer_b200.config import make_config
     m = BoxDreamer(make_config())
     with pytest.raises(_lib.BoxDreamerLibError):
         m(synth.synth_inputs(1, 2))
 
 
 def test_state_dict_layout_matches_reference_contract():
-    from oracle.ref_import import make_config
+    from boxdreamer_b200.config import make_config
     m = BoxDreamer(make_config())
     sd = m.state_dict()
     exp = synth.decoder_param_shapes()
@@ -56,7 +56,7 @@ def test_state_dict_layout_matches_reference_contract():
 
 
 def test_config_validation_mirrors_reference():
-    from oracle.ref_import import make_config
+    from boxdreamer_b200.config import make_config
     cfg = make_config()
     cfg["modules"]["decoder"]["patch_size"] = 16
     with pytest.raises(AssertionError):
@@ -80,7 +80,7 @@ def test_synth_inputs_contract():
 
 def test_interpolated_pos_embed_matches_oracle():
     from oracle import boxdreamer_oracle as O
-    from oracle.ref_import import make_config
+    from boxdreamer_b200.config import make_config
     m = BoxDreamer(make_config())
     dino = synth.synth_dino_state_dict(0)
     m.rgb_encoder.model.load_state_dict(dino)

@@ -18,7 +18,7 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
 def _config(img_size=224):
-    from oracle.ref_import import make_config  # config tree only; does not import the reference
+    from boxdreamer_b200.config import make_config
     return make_config(img_size)
 
 

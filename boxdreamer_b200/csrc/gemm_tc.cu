@@ -43,22 +43,41 @@ struct GemmArgs {
 };
 
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  // 0.5 x (1 + erf(x / sqrt 2)); erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below bf16 resolution)
-  float z = fabsf(x) * 0.70710678118654752f;
-  float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
-  float er = 1.0f - poly * __expf(-z * z);
-  er = copysignf(er, x);
-  return 0.5f * x * (1.0f + er);
+  // x * Phi(x) with Phi(x) - 0.5 = 0.5 erf(x / sqrt 2) as a degree-17 odd minimax polynomial on |x| <= 4 (clamped beyond,
+  // where Phi - 0.5 = +-0.49997): max |gelu error| 2.2e-5 in fp32 Horner form -- two orders below bf16 resolution --
+  // and no MUFU op, so the fc1 epilogue stays off the 16/clk/SM special-function pipe.
+  const float xc = fminf(fmaxf(x, -4.0f), 4.0f);
+  const float x2 = xc * xc;
+  float p = 8.062929977e-11f;
+  p = fmaf(p, x2, -7.003156417e-09f);
+  p = fmaf(p, x2, 2.716075885e-07f);
+  p = fmaf(p, x2, -6.294891059e-06f);
+  p = fmaf(p, x2, 9.890726931e-05f);
+  p = fmaf(p, x2, -1.133918807e-03f);
+  p = fmaf(p, x2, 9.877469438e-03f);
+  p = fmaf(p, x2, -6.641058494e-02f);
+  p = fmaf(p, x2, 3.989227133e-01f);
+  return x * fmaf(p, xc, 0.5f);
 }
 
-// staging tile: 32 rows x 32 words, XOR-swizzled so both the row-owner writes and the row-wise reads are conflict-free
+// staging tile: 32 rows x 32 words (128 B per row).  Two access patterns share it:
+//  (a) word-granular XOR swizzle (stage_write / stage_read): row-owner writes, row-wise 4-byte reads  (EPI_QKV)
+//  (b) 16-byte-chunk XOR swizzle (stage_write16 / stage_read16): row-owner writes 8 x 16 B, then each lane reads a
+//      16-byte chunk of 8 different rows -> 4 rows x 128 B per warp instruction, conflict-free both ways.
 __device__ __forceinline__ void stage_write(uint32_t* tile, int lane, const uint32_t (&w)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) tile[lane * 32 + (j ^ lane)] = w[j];
 }
 __device__ __forceinline__ uint32_t stage_read(const uint32_t* tile, int rr, int lane) {
   return tile[rr * 32 + (lane ^ rr)];
+}
+__device__ __forceinline__ void stage_write16(uint32_t* tile, int lane, const uint32_t (&w)[32]) {
+  uint4* row = reinterpret_cast<uint4*>(tile + lane * 32);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) row[j ^ (lane & 7)] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+}
+__device__ __forceinline__ uint4 stage_read16(const uint32_t* tile, int row, int c4) {
+  return reinterpret_cast<const uint4*>(tile + row * 32)[c4 ^ (row & 7)];
 }
 
 template <int BN, int EPI, int HD>
@@ -175,80 +194,85 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
 
-      if constexpr (EPI == EPI_F32 || EPI == EPI_RESID) {
-        // per-lane output row (with optional remap) fetched by shuffle in the row-wise phase
+      if constexpr (EPI != EPI_QKV) {
+        // 32-column chunks.  Row-owner phase: TMEM -> registers -> swizzled smem.  Row-wise phase: lane = (row group
+        // rsub, 16-byte column chunk c4); 8 independent 16-byte global accesses per lane are in flight at once.
         long long my_out_row = my_row;
         int my_tab_row = 0;
         if (EPI == EPI_F32 && e.rp_in > 0) {
           my_tab_row = my_row % e.rp_in;
           my_out_row = static_cast<long long>(my_row / e.rp_in) * e.rp_out + e.rp_off + my_tab_row;
         }
+        const int c4 = lane & 7, rsub = lane >> 3;
         constexpr int NCH = BN / 64;  // chunks of 32 columns per column-half
         for (int c = 0; c < NCH; ++c) {
           const int col0 = n_blk * BN + grp * (BN / 2) + c * 32;
-          if (col0 >= N) {  // whole chunk out of range (N tail): still must drain nothing; just skip
-            continue;
-          }
+          if (col0 >= N) continue;  // N tail: nothing to store (warp-uniform)
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_acc + grp * (BN / 2) + c * 32, v);
           tmem_wait_ld();
-          stage_write(tile_s, lane, v);
+          stage_write16(tile_s, lane, v);
           __syncwarp();
-          const int col = col0 + lane;
-          const bool col_ok = col < N;
-          const float bcol = col_ok ? __ldg(e.bias + col) : 0.f;
-          const float gcol = (EPI == EPI_RESID && e.gamma && col_ok) ? __ldg(e.gamma + col) : 1.f;
-#pragma unroll 4
-          for (int rr = 0; rr < 32; ++rr) {
-            const float a = __uint_as_float(stage_read(tile_s, rr, lane)) + bcol;
-            const long long orow = __shfl_sync(0xffffffffu, my_out_row, rr);
-            const int trow = __shfl_sync(0xffffffffu, my_tab_row, rr);
-            if (row_w + rr < M && col_ok) {
-              float* dst = e.out_f32 + orow * e.ldo + col;
-              if constexpr (EPI == EPI_F32) {
-                float add = (e.addtab != nullptr) ? __ldg(e.addtab + static_cast<long long>(trow) * N + col) : 0.f;
-                *dst = a + add;
-              } else {
-                *dst = *dst + gcol * a;
+          const int col = col0 + 4 * c4;
+          const bool col_ok = col < N;  // N % 4 == 0: a 16-byte chunk is entirely in or out
+          const float4 b4 = col_ok ? __ldg(reinterpret_cast<const float4*>(e.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 a[8];
+          long long orow[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + rsub;
+            const uint4 u = stage_read16(tile_s, row, c4);
+            a[i] = make_float4(__uint_as_float(u.x) + b4.x, __uint_as_float(u.y) + b4.y, __uint_as_float(u.z) + b4.z,
+                               __uint_as_float(u.w) + b4.w);
+            orow[i] = __shfl_sync(0xffffffffu, my_out_row, row);
+          }
+          if constexpr (EPI == EPI_F32) {
+            int trow[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) trow[i] = __shfl_sync(0xffffffffu, my_tab_row, 4 * i + rsub);
+            if (e.addtab != nullptr && col_ok) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (row_w + 4 * i + rsub < M) {
+                  const float4 t4 = __ldg(reinterpret_cast<const float4*>(e.addtab + static_cast<long long>(trow[i]) * N + col));
+                  a[i].x += t4.x; a[i].y += t4.y; a[i].z += t4.z; a[i].w += t4.w;
+                }
               }
             }
-          }
-          __syncwarp();
-        }
-      } else if constexpr (EPI == EPI_GELU || EPI == EPI_ACT) {
-        constexpr int NCH = BN / 128;  // chunks of 64 columns per column-half
-        bf16* out = reinterpret_cast<bf16*>(e.out_act);
-        for (int c = 0; c < NCH; ++c) {
-          const int col0 = n_blk * BN + grp * (BN / 2) + c * 64;
-          if (col0 >= N) continue;
-          uint32_t v0[32], v1[32], w[32];
-          tmem_ld_32x32b_x32(t_acc + grp * (BN / 2) + c * 64, v0);
-          tmem_ld_32x32b_x32(t_acc + grp * (BN / 2) + c * 64 + 32, v1);
-          tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a0 = __uint_as_float(v0[2 * j]) + __ldg(e.bias + min(col0 + 2 * j, N - 1));
-            float a1 = __uint_as_float(v0[2 * j + 1]) + __ldg(e.bias + min(col0 + 2 * j + 1, N - 1));
-            float b0 = __uint_as_float(v1[2 * j]) + __ldg(e.bias + min(col0 + 32 + 2 * j, N - 1));
-            float b1 = __uint_as_float(v1[2 * j + 1]) + __ldg(e.bias + min(col0 + 32 + 2 * j + 1, N - 1));
-            if constexpr (EPI == EPI_GELU) {
-              a0 = gelu_erf_fast(a0); a1 = gelu_erf_fast(a1); b0 = gelu_erf_fast(b0); b1 = gelu_erf_fast(b1);
+            for (int i = 0; i < 8; ++i) {
+              if (row_w + 4 * i + rsub < M && col_ok) *reinterpret_cast<float4*>(e.out_f32 + orow[i] * e.ldo + col) = a[i];
             }
-            w[j] = pack_bf16x2(a0, a1);
-            w[16 + j] = pack_bf16x2(b0, b1);
-          }
-          stage_write(tile_s, lane, w);
-          __syncwarp();
-          const int col = col0 + 2 * lane;
-#pragma unroll 4
-          for (int rr = 0; rr < 32; ++rr) {
-            const uint32_t word = stage_read(tile_s, rr, lane);
-            const long long row = row_w + rr;
-            if (row < M) {
-              if (col + 1 < N) {
-                *reinterpret_cast<uint32_t*>(out + row * N + col) = word;
-              } else if (col < N) {
-                out[row * N + col] = __ushort_as_bfloat16(static_cast<unsigned short>(word & 0xffffu));
+          } else if constexpr (EPI == EPI_RESID) {
+            const float4 g4 = (e.gamma != nullptr && col_ok) ? __ldg(reinterpret_cast<const float4*>(e.gamma + col))
+                                                              : make_float4(1.f, 1.f, 1.f, 1.f);
+            float4 r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {  // all residual loads first (memory-level parallelism), then the stores
+              r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row_w + 4 * i + rsub < M && col_ok) r[i] = *reinterpret_cast<const float4*>(e.out_f32 + orow[i] * e.ldo + col);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (row_w + 4 * i + rsub < M && col_ok) {
+                r[i].x = fmaf(g4.x, a[i].x, r[i].x); r[i].y = fmaf(g4.y, a[i].y, r[i].y);
+                r[i].z = fmaf(g4.z, a[i].z, r[i].z); r[i].w = fmaf(g4.w, a[i].w, r[i].w);
+                *reinterpret_cast<float4*>(e.out_f32 + orow[i] * e.ldo + col) = r[i];
+              }
+            }
+          } else {  // EPI_GELU / EPI_ACT: bf16 store, 8 bytes per lane
+            bf16* out = reinterpret_cast<bf16*>(e.out_act);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if constexpr (EPI == EPI_GELU) {
+                a[i].x = gelu_erf_fast(a[i].x); a[i].y = gelu_erf_fast(a[i].y);
+                a[i].z = gelu_erf_fast(a[i].z); a[i].w = gelu_erf_fast(a[i].w);
+              }
+              if (row_w + 4 * i + rsub < M && col_ok) {
+                uint2 pk;
+                pk.x = pack_bf16x2(a[i].x, a[i].y);
+                pk.y = pack_bf16x2(a[i].z, a[i].w);
+                *reinterpret_cast<uint2*>(out + orow[i] * N + col) = pk;
               }
             }
           }
@@ -433,7 +457,10 @@ static cudaError_t launch(const bf16* A, const bf16* W, int M, int N, int K, con
 }
 
 cudaError_t gemm_tc(const bf16* A, const bf16* W, int M, int N, int K, int epi, const GemmEpi& e, cudaStream_t s) {
-  if (M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0) { g_tc_err = "gemm_tc: K must be a positive multiple of 8"; return cudaErrorInvalidValue; }
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0 || (N % 4) != 0) {
+    g_tc_err = "gemm_tc: K must be a positive multiple of 8 and N a multiple of 4";
+    return cudaErrorInvalidValue;
+  }
   switch (epi) {
     case EPI_F32: return launch<256, EPI_F32, 32>(A, W, M, N, K, e, s);
     case EPI_RESID: return launch<256, EPI_RESID, 32>(A, W, M, N, K, e, s);

@@ -108,7 +108,7 @@ BD_HD void jacobi_eig_sym12(double* A, double* V) {
       dg += A[i * 13] * A[i * 13];
       for (int j = i + 1; j < 12; ++j) off += A[i * 12 + j] * A[i * 12 + j];
     }
-    if (off <= 1e-60 * dg || off == 0.0) break;
+    if (off <= 1e-36 * dg || off == 0.0) break;  // off-diagonal below fp64 resolution of the diagonal
     for (int p = 0; p < 11; ++p) {
       for (int q = p + 1; q < 12; ++q) {
         const double apq = A[p * 12 + q];

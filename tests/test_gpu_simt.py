@@ -102,8 +102,10 @@ def test_corners_topk_matches_oracle(lib):
 
 
 def _rot_err_deg(Ra, Rb):
-    c = (np.trace(Ra.T @ Rb) - 1) / 2
-    return float(np.degrees(np.arccos(np.clip(c, -1, 1))))
+    """Geodesic angle between two rotations, computed from the chordal distance so that it stays accurate for the
+    float32-rounded matrices the C ABI returns (acos((tr-1)/2) loses half the digits near 0)."""
+    s = min(np.linalg.norm(np.asarray(Ra, dtype=np.float64) - np.asarray(Rb, dtype=np.float64)) / (2.0 * np.sqrt(2.0)), 1.0)
+    return float(np.degrees(2.0 * np.arcsin(s)))
 
 
 def test_pnp_matches_cv2_fixture(lib):

@@ -220,87 +220,143 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+// d == 768 fast path: the row lives in registers (6 x float4 per lane): one HBM read, one write
+__global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ b, float eps, float* __restrict__ out_f32,
+                                                           bf16* __restrict__ out_bf16, int rows_out, int rows_out_per,
+                                                           int rows_in_per, int row_off) {
+  constexpr int D = 768;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows_out) return;
+  long long rin = r;
+  if (rows_out_per > 0) rin = static_cast<long long>(r / rows_out_per) * rows_in_per + row_off + (r % rows_out_per);
+  const float4* xr = reinterpret_cast<const float4*>(x + rin * D);
+  float4 v[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) v[i] = xr[lane + 32 * i];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.0f / D);
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    var = fmaf(v[i].x, v[i].x, var); var = fmaf(v[i].y, v[i].y, var);
+    var = fmaf(v[i].z, v[i].z, var); var = fmaf(v[i].w, v[i].w, var);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var * (1.0f / D) + eps);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    float4 o = make_float4(v[i].x * rstd, v[i].y * rstd, v[i].z * rstd, v[i].w * rstd);
+    if (w) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(b + c));
+      o.x = fmaf(o.x, w4.x, b4.x); o.y = fmaf(o.y, w4.y, b4.y); o.z = fmaf(o.z, w4.z, b4.z); o.w = fmaf(o.w, w4.w, b4.w);
+    }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + static_cast<long long>(r) * D + c) = o;
+    if (out_bf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(r) * D + c) = pk;
+    }
+  }
+}
+
 cudaError_t layernorm(const float* x, const float* w, const float* b, float eps, float* out_f32, bf16* out_bf16, int rows_out,
                       int d, int rows_out_per, int rows_in_per, int row_off, cudaStream_t s) {
-  layernorm_kernel<<<(rows_out + 7) / 8, 256, 0, s>>>(x, w, b, eps, out_f32, out_bf16, rows_out, d, rows_out_per, rows_in_per,
-                                                      row_off);
+  if (d == 768)
+    layernorm768_kernel<<<(rows_out + 7) / 8, 256, 0, s>>>(x, w, b, eps, out_f32, out_bf16, rows_out, rows_out_per, rows_in_per,
+                                                           row_off);
+  else
+    layernorm_kernel<<<(rows_out + 7) / 8, 256, 0, s>>>(x, w, b, eps, out_f32, out_bf16, rows_out, d, rows_out_per, rows_in_per,
+                                                        row_off);
   return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
 // im2col for the 14x14/s14 patch-embed conv with the ImageNet normalisation folded in
-// (encoder/dinov2.py:45-46, DINOv2 layers/patch_embed.py:65-78).  Column order (c, pr, pc) = conv weight order.
+// (encoder/dinov2.py:45-46, DINOv2 layers/patch_embed.py:65-78) and patchify of the 8-channel corner heat maps
+// (betr.py:211-228).  One CTA per (image, patch row): the C x 14 image rows are read coalesced into shared memory,
+// then the 16 (or S/14) output token rows -- one contiguous block of the GEMM A operand -- are written coalesced.
+//   MODE 0 (im2col)  : column = c*p*p + pr*p + pc   (conv weight order), value = (x - mean_c) / std_c, zero pad to kpad
+//   MODE 1 (patchify): column = (pr*p + pc)*C + c   (einsum "nchpwq->nhwpqc")
 
-template <typename TIn, typename TOut>
-__global__ void im2col_kernel(const TIn* __restrict__ img, TOut* __restrict__ out, int L, int S, int patch, int kpad) {
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+template <typename TIn, typename TOut, int MODE>
+__global__ void __launch_bounds__(256) patch_rows_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int C, int S, int patch,
+                                                         int kout) {
+  extern __shared__ unsigned char smem_raw[];
+  TOut* tile = reinterpret_cast<TOut*>(smem_raw);
   const int g = S / patch;
-  const long long total = static_cast<long long>(L) * g * g * kpad;
-  if (idx >= total) return;
-  const int col = static_cast<int>(idx % kpad);
-  const long long rowi = idx / kpad;
-  const int kreal = 3 * patch * patch;
-  float v = 0.f;
-  if (col < kreal) {
-    const int c = col / (patch * patch), rem = col % (patch * patch);
-    const int pr = rem / patch, pc = rem % patch;
-    const int pw = static_cast<int>(rowi % g), ph = static_cast<int>((rowi / g) % g);
-    const long long l = rowi / (g * g);
-    const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
-    const float stdv = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
-    const float x = static_cast<float>(img[((l * 3 + c) * S + ph * patch + pr) * S + pw * patch + pc]);
-    v = (x - mean) / stdv;
+  const int ph = blockIdx.x;
+  const long long l = blockIdx.y;
+  const int pitch = S + 2;  // de-conflicts the channel-strided reads of MODE 1
+  const int nrows = C * patch;
+  for (int idx = threadIdx.x; idx < nrows * S; idx += blockDim.x) {
+    const int row = idx / S, x = idx % S;
+    const int c = row / patch, pr = row % patch;
+    float v = static_cast<float>(in[((l * C + c) * S + ph * patch + pr) * S + x]);
+    if (MODE == 0) {
+      const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+      const float stdv = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+      v = (v - mean) / stdv;
+    }
+    tile[row * pitch + x] = static_cast<TOut>(v);
   }
-  out[idx] = static_cast<TOut>(v);
+  __syncthreads();
+  TOut* dst = out + (l * g * g + static_cast<long long>(ph) * g) * kout;
+  const int kreal = C * patch * patch;
+  for (int idx = threadIdx.x; idx < g * kout; idx += blockDim.x) {
+    const int pw = idx / kout, col = idx % kout;
+    TOut v = static_cast<TOut>(0.f);
+    if (col < kreal) {
+      int c, pr, pc;
+      if (MODE == 0) { c = col / (patch * patch); const int rem = col % (patch * patch); pr = rem / patch; pc = rem % patch; }
+      else { c = col % C; const int pp = col / C; pr = pp / patch; pc = pp % patch; }
+      v = tile[(c * patch + pr) * pitch + pw * patch + pc];
+    }
+    dst[idx] = v;
+  }
+}
+
+template <typename TIn, typename TOut, int MODE>
+static cudaError_t launch_patch_rows(const void* in, void* out, int L, int C, int S, int patch, int kout, cudaStream_t s) {
+  const size_t smem = static_cast<size_t>(C) * patch * (S + 2) * sizeof(TOut);
+  auto kern = patch_rows_kernel<TIn, TOut, MODE>;
+  if (smem > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+  }
+  dim3 grid(S / patch, L);
+  kern<<<grid, 256, smem, s>>>(reinterpret_cast<const TIn*>(in), reinterpret_cast<TOut*>(out), C, S, patch, kout);
+  return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t dispatch_patch_rows(const void* in, int in_bf16, void* out, int out_bf16, int L, int C, int S, int patch, int kout,
+                                       cudaStream_t s) {
+  if (in_bf16 && out_bf16) return launch_patch_rows<bf16, bf16, MODE>(in, out, L, C, S, patch, kout, s);
+  if (in_bf16) return launch_patch_rows<bf16, float, MODE>(in, out, L, C, S, patch, kout, s);
+  if (out_bf16) return launch_patch_rows<float, bf16, MODE>(in, out, L, C, S, patch, kout, s);
+  return launch_patch_rows<float, float, MODE>(in, out, L, C, S, patch, kout, s);
 }
 
 cudaError_t im2col_patches(const void* images, int img_is_bf16, void* out, int out_is_bf16, int L, int S, int patch, int kpad,
                            cudaStream_t s) {
-  const int g = S / patch;
-  const long long total = static_cast<long long>(L) * g * g * kpad;
-  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-  if (img_is_bf16 && out_is_bf16)
-    im2col_kernel<bf16, bf16><<<blocks, 256, 0, s>>>(reinterpret_cast<const bf16*>(images), reinterpret_cast<bf16*>(out), L, S, patch, kpad);
-  else if (img_is_bf16)
-    im2col_kernel<bf16, float><<<blocks, 256, 0, s>>>(reinterpret_cast<const bf16*>(images), reinterpret_cast<float*>(out), L, S, patch, kpad);
-  else if (out_is_bf16)
-    im2col_kernel<float, bf16><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(images), reinterpret_cast<bf16*>(out), L, S, patch, kpad);
-  else
-    im2col_kernel<float, float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(images), reinterpret_cast<float*>(out), L, S, patch, kpad);
-  return cudaGetLastError();
-}
-
-// patchify of the 8-channel corner heatmaps (betr.py:211-228): per-token feature order (pr, pc, c)
-template <typename TIn, typename TOut>
-__global__ void patchify_kernel(const TIn* __restrict__ feat, TOut* __restrict__ out, int L, int C, int S, int patch) {
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const int g = S / patch;
-  const int kk = patch * patch * C;
-  const long long total = static_cast<long long>(L) * g * g * kk;
-  if (idx >= total) return;
-  const int col = static_cast<int>(idx % kk);
-  const long long rowi = idx / kk;
-  const int c = col % C, pp = col / C;
-  const int pr = pp / patch, pc = pp % patch;
-  const int pw = static_cast<int>(rowi % g), ph = static_cast<int>((rowi / g) % g);
-  const long long l = rowi / (g * g);
-  out[idx] = static_cast<TOut>(static_cast<float>(feat[((l * C + c) * S + ph * patch + pr) * S + pw * patch + pc]));
+  return dispatch_patch_rows<0>(images, img_is_bf16, out, out_is_bf16, L, 3, S, patch, kpad, s);
 }
 
 cudaError_t patchify_heat(const void* feat, int in_is_bf16, void* out, int out_is_bf16, int L, int C, int S, int patch,
                           cudaStream_t s) {
-  const int g = S / patch;
-  const long long total = static_cast<long long>(L) * g * g * patch * patch * C;
-  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-  if (in_is_bf16 && out_is_bf16)
-    patchify_kernel<bf16, bf16><<<blocks, 256, 0, s>>>(reinterpret_cast<const bf16*>(feat), reinterpret_cast<bf16*>(out), L, C, S, patch);
-  else if (in_is_bf16)
-    patchify_kernel<bf16, float><<<blocks, 256, 0, s>>>(reinterpret_cast<const bf16*>(feat), reinterpret_cast<float*>(out), L, C, S, patch);
-  else if (out_is_bf16)
-    patchify_kernel<float, bf16><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(feat), reinterpret_cast<bf16*>(out), L, C, S, patch);
-  else
-    patchify_kernel<float, float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(feat), reinterpret_cast<float*>(out), L, C, S, patch);
-  return cudaGetLastError();
+  return dispatch_patch_rows<1>(feat, in_is_bf16, out, out_is_bf16, L, C, S, patch, patch * patch * C, s);
 }
 
 // DINOv2 prepare_tokens (vision_transformer.py:213-232): row 0 = cls + pos[0]; rows 1..n_reg = register tokens

@@ -305,7 +305,7 @@ BD_HD void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int m
     }
     bool improved = false;
     double step = 0.0, dc = 0.0;
-    for (int tr = 0; tr < 30; ++tr) {
+    for (int tr = 0; tr < 12; ++tr) {
       double delta[6];
       if (!solve6(H, g, lam, delta)) { lam *= 10.0; continue; }
       const double w[3] = {delta[0], delta[1], delta[2]};
@@ -334,7 +334,7 @@ BD_HD void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int m
       }
       lam *= 10.0;
     }
-    if (!improved || step < 1e-14 || dc <= 1e-30) break;
+    if (!improved || step < 1e-13 || dc <= 1e-15 * cost + 1e-300) break;
   }
   nearest_rotation(R, 4);
 }

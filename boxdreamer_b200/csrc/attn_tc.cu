@@ -313,6 +313,7 @@ static cudaError_t launch_att(const bf16* Q, const bf16* K, const bf16* Vt, bf16
 cudaError_t attention_tc(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int head_dim, int seq,
                          int seq_pad, float scale, int variant, cudaStream_t s) {
   if (seq_pad % 128 != 0 || seq > seq_pad) return cudaErrorInvalidValue;
+  if (variant == 2) return attention_tc2(Q, K, Vt, O, L, heads, head_dim, seq, seq_pad, scale, s);
   if (head_dim == 96) {
     if (variant == 1) return launch_att<96, 128, true>(Q, K, Vt, O, L, heads, seq, seq_pad, scale, s);
     return launch_att<96, 64, false>(Q, K, Vt, O, L, heads, seq, seq_pad, scale, s);

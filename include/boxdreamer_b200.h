@@ -54,7 +54,7 @@ typedef struct {
   int32_t dino_registers;  /* 4                                                */
   int32_t dino_pretrain_grid; /* 37 (pos_embed is 1 + 37*37 rows)              */
   int32_t precision;       /* bd_precision                                     */
-  int32_t attn_variant;    /* 0: P through shared memory, 1: P through tensor memory */
+  int32_t attn_variant;    /* 0: P through shared memory, 1: P through tensor memory, 2: persistent ping-pong kernel */
   int32_t max_batch;       /* B the workspace is sized for                     */
   int32_t max_views;       /* T (references + query)                           */
 } bd_config;

@@ -105,6 +105,11 @@ def test_attention_tc_p_in_tmem(lib, L, seq, heads, hd):
     _attention_case(lib, 1, L, seq, heads, hd)
 
 
+@pytest.mark.parametrize("L,seq,heads,hd", ATT_CASES + [(5, 261, 12, 64), (3, 100, 8, 96), (1, 2000, 8, 96), (40, 261, 12, 64)])
+def test_attention_tc_pingpong(lib, L, seq, heads, hd):
+    _attention_case(lib, 2, L, seq, heads, hd)
+
+
 def _attention_case(lib, variant, L, seq, heads, hd):
     seq_pad = (seq + 127) // 128 * 128
     g = torch.Generator().manual_seed(seq + hd + variant)

@@ -18,7 +18,7 @@ namespace bd {
 
 bool get_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t bc, uint32_t br);
 
-static constexpr int A2_THREADS = 320;
+static constexpr int A2_THREADS = 384;  // 3 warpgroups: {TMA, MMA, -, -}, softmax tile 0, softmax tile 1
 static constexpr int A2_BQ = 128;
 static constexpr int A2_BKV = 128;
 
@@ -30,16 +30,20 @@ struct Att2Cfg {
   static constexpr int V_SUB = HD * 128;
   static constexpr int V_TILE = 2 * V_SUB;
   static constexpr int NSTG = (HD > 64) ? 2 : 4;
+  static constexpr int QBUF = (HD > 64) ? 1 : 2;   // item-level Q buffering: the next item's Q is prefetched when smem allows
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 2 * Q_TILE + NSTG * (K_TILE + V_TILE) + BAR_BYTES + 1024;
+  static constexpr int SMEM_BYTES = QBUF * 2 * Q_TILE + NSTG * (K_TILE + V_TILE) + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 512;
 };
 
 struct Att2Args {
   bf16* O;
   int heads, seq, seq_pad, BH;
+  int q_off;         // first query row handled by this kernel (rows [0, q_off) are done by attention_prefix_rows)
   float scale_log2;
+  long long* trace;  // debug: per-role clock64 stamps of CTA 0's first items (nullptr in production)
 };
+#define A2_TRACE(role, slot) do { if (args.trace != nullptr && blockIdx.x == 0 && (slot) < 512) args.trace[(role) * 512 + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t s_col(int g) { return static_cast<uint32_t>(g * 128); }
 __device__ __forceinline__ uint32_t o_col(int g) { return static_cast<uint32_t>(256 + g * 128); }
@@ -52,13 +56,14 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int NSTG = Cfg::NSTG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                  // [2][Q_TILE]
-  uint8_t* sK = sQ + 2 * Cfg::Q_TILE;                  // [NSTG][K_TILE]
+  constexpr int QBUF = Cfg::QBUF;
+  uint8_t* sQ = smem;                                  // [QBUF][2][Q_TILE]
+  uint8_t* sK = sQ + QBUF * 2 * Cfg::Q_TILE;           // [NSTG][K_TILE]
   uint8_t* sV = sK + NSTG * Cfg::K_TILE;               // [NSTG][V_TILE]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NSTG * Cfg::V_TILE);
-  uint64_t* q_full = bars;                  // [2]
-  uint64_t* q_empty = bars + 2;             // [1]
-  uint64_t* k_full = bars + 3;              // [NSTG]
+  uint64_t* q_full = bars;                  // [QBUF][2]
+  uint64_t* q_empty = bars + 4;             // [QBUF]
+  uint64_t* k_full = bars + 6;              // [NSTG]
   uint64_t* k_empty = k_full + NSTG;
   uint64_t* v_full = k_empty + NSTG;
   uint64_t* v_empty = v_full + NSTG;
@@ -70,7 +75,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int seq = args.seq, seq_pad = args.seq_pad;
-  const int n_qt = (seq + A2_BQ - 1) / A2_BQ;            // query tiles per sequence
+  const int q_off = args.q_off;
+  const int n_qt = (seq - q_off + A2_BQ - 1) / A2_BQ;    // query tiles per sequence
   const int n_pairs = (n_qt + 1) / 2;
   const int n_items = args.BH * n_pairs;
   const int n_kv = (seq + A2_BKV - 1) / A2_BKV;
@@ -81,9 +87,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(&q_full[0], 1);
-    mbar_init(&q_full[1], 1);
-    mbar_init(q_empty, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&q_full[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&q_empty[i], 1);
     for (int i = 0; i < NSTG; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -106,6 +111,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // register budget: the two softmax warpgroups keep a whole 128-column S row per thread
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -114,17 +122,19 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       int it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int bh = item / n_pairs, pair = item % n_pairs;
-        const int q0 = pair * 2 * A2_BQ;
+        const int q0 = q_off + pair * 2 * A2_BQ;
         const bool act1 = q0 + A2_BQ < seq;
-        mbar_wait(q_empty, (it & 1) ^ 1);  // previous item's S MMAs have consumed Q
-        mbar_expect_tx(&q_full[0], Cfg::Q_TILE);
+        const int qb = it % QBUF;
+        uint8_t* sQi = sQ + qb * 2 * Cfg::Q_TILE;
+        mbar_wait(&q_empty[qb], ((it / QBUF) & 1) ^ 1);  // the item that used this Q buffer has issued all its S MMAs
+        mbar_expect_tx(&q_full[qb * 2 + 0], Cfg::Q_TILE);
 #pragma unroll
-        for (int s = 0; s < Cfg::NQS; ++s) tma_load_2d(sQ + s * (A2_BQ * 128), &tmQ, &q_full[0], s * 64, bh * seq_pad + q0);
+        for (int s = 0; s < Cfg::NQS; ++s) tma_load_2d(sQi + s * (A2_BQ * 128), &tmQ, &q_full[qb * 2 + 0], s * 64, bh * seq_pad + q0);
         if (act1) {
-          mbar_expect_tx(&q_full[1], Cfg::Q_TILE);
+          mbar_expect_tx(&q_full[qb * 2 + 1], Cfg::Q_TILE);
 #pragma unroll
           for (int s = 0; s < Cfg::NQS; ++s)
-            tma_load_2d(sQ + Cfg::Q_TILE + s * (A2_BQ * 128), &tmQ, &q_full[1], s * 64, bh * seq_pad + q0 + A2_BQ);
+            tma_load_2d(sQi + Cfg::Q_TILE + s * (A2_BQ * 128), &tmQ, &q_full[qb * 2 + 1], s * 64, bh * seq_pad + q0 + A2_BQ);
         }
         for (int j = 0; j < n_kv; ++j) {
           mbar_wait(&k_empty[st], ph ^ 1);
@@ -148,7 +158,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       int st = 0;
       uint32_t ph = 0;
       uint32_t p_cnt[2] = {0, 0};
-      uint32_t q1_cnt = 0;  // q_full[1] / o_full[1] only complete for items whose second tile is active
+      uint32_t q1_cnt[2] = {0, 0};  // q_full[.][1] only completes for items whose second tile is active
+      const uint8_t* sQi = sQ;
       int it = 0;
 
       auto issue_s = [&](int g, int stage, int ncols) {
@@ -156,7 +167,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t d = tmem_base + s_col(g);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
-          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sQ + g * Cfg::Q_TILE + (k / 4) * (A2_BQ * 128))) + 2 * (k % 4);
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sQi + g * Cfg::Q_TILE + (k / 4) * (A2_BQ * 128))) + 2 * (k % 4);
           const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + stage * Cfg::K_TILE + (k / 4) * (A2_BKV * 128))) + 2 * (k % 4);
           umma_ss_bf16(d, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
         }
@@ -171,73 +182,92 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       };
 
+      // Issue order (tile 1 trails tile 0 by one step so the two softmax groups alternate on the MUFU pipe instead of
+      // running in lock-step):
+      //   S0(0) | j=0: PV0(0) S0(1) S1(0) | j: PV0(j) S0(j+1) PV1(j-1) S1(j) | ... | PV1(n-1)
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int pair = item % n_pairs;
-        const int q0 = pair * 2 * A2_BQ;
+        const int q0 = q_off + pair * 2 * A2_BQ;
         const bool act1 = q0 + A2_BQ < seq;
-        mbar_wait(&q_full[0], it & 1);
+        const int qb = it % QBUF;
+        uint64_t* q_empty_i = &q_empty[qb];
+        sQi = sQ + qb * 2 * Cfg::Q_TILE;
+        mbar_wait(&q_full[qb * 2 + 0], (it / QBUF) & 1);
         if (act1) {
-          mbar_wait(&q_full[1], q1_cnt & 1);
-          ++q1_cnt;
+          mbar_wait(&q_full[qb * 2 + 1], q1_cnt[qb] & 1);
+          ++q1_cnt[qb];
         }
-        // prologue: S0(0), S1(0)
-        {
-          const int nc = (n_kv == 1) ? tail_cols : A2_BKV;
-          mbar_wait(&k_full[st], ph);
-          tc_fence_after();
-          issue_s(0, st, nc);
-          umma_commit(&s_full[0]);
-          if (act1) {
-            issue_s(1, st, nc);
-            umma_commit(&s_full[1]);
-          }
+        mbar_wait(&k_full[st], ph);
+        tc_fence_after();
+        issue_s(0, st, (n_kv == 1) ? tail_cols : A2_BKV);
+        umma_commit(&s_full[0]);
+        if (!act1) {  // tile 1 inactive: K_0 is only read by S0(0)
           umma_commit(&k_empty[st]);
-          if (n_kv == 1) umma_commit(q_empty);
+          if (n_kv == 1) umma_commit(q_empty_i);
         }
+        int st_prev = st;  // stage of K/V tile j-1 (still needed by tile 1)
         for (int j = 0; j < n_kv; ++j) {
           const int nc = (j == n_kv - 1) ? tail_cols : A2_BKV;
           const bool has_next = j + 1 < n_kv;
           const int st_next = (st + 1 == NSTG) ? 0 : st + 1;
           const uint32_t ph_next = (st + 1 == NSTG) ? (ph ^ 1) : ph;
           const int nc_next = (j + 1 == n_kv - 1) ? tail_cols : A2_BKV;
+          // ---- tile 0: O0 += P0(j) V_j, then S0(j+1) ----
           mbar_wait(&v_full[st], ph);
-          // ---- tile 0: O0 += P0 V_j ; then S0 of the next K tile ----
+          A2_TRACE(0, (it * n_kv + j) * 4 + 0);
           mbar_wait(&p_full[0], p_cnt[0] & 1);
+          A2_TRACE(0, (it * n_kv + j) * 4 + 1);
           ++p_cnt[0];
           tc_fence_after();
           issue_pv(0, st, nc, j == 0);
           if (!has_next) umma_commit(&o_full[0]);
+          if (!act1) umma_commit(&v_empty[st]);
           if (has_next) {
             mbar_wait(&k_full[st_next], ph_next);
             tc_fence_after();
             issue_s(0, st_next, nc_next);
             umma_commit(&s_full[0]);
-          }
-          // ---- tile 1 ----
-          if (act1) {
-            mbar_wait(&p_full[1], p_cnt[1] & 1);
-            ++p_cnt[1];
-            tc_fence_after();
-            issue_pv(1, st, nc, j == 0);
-            if (!has_next) umma_commit(&o_full[1]);
-          }
-          umma_commit(&v_empty[st]);
-          if (has_next) {
-            if (act1) {
-              issue_s(1, st_next, nc_next);
-              umma_commit(&s_full[1]);
+            if (!act1) {
+              umma_commit(&k_empty[st_next]);
+              if (j + 1 == n_kv - 1) umma_commit(q_empty_i);
             }
-            umma_commit(&k_empty[st_next]);
-            if (j + 1 == n_kv - 1) umma_commit(q_empty);  // last S MMAs of this item issued
           }
+          // ---- tile 1, one step behind: O1 += P1(j-1) V_{j-1}, then S1(j) ----
+          if (act1) {
+            if (j > 0) {
+              const int ncp = A2_BKV;  // tile j-1 is never the last one here
+              A2_TRACE(0, (it * n_kv + j) * 4 + 2);
+              mbar_wait(&p_full[1], p_cnt[1] & 1);
+              A2_TRACE(0, (it * n_kv + j) * 4 + 3);
+              ++p_cnt[1];
+              tc_fence_after();
+              issue_pv(1, st_prev, ncp, j == 1);
+              umma_commit(&v_empty[st_prev]);
+            }
+            issue_s(1, st, nc);
+            umma_commit(&s_full[1]);
+            umma_commit(&k_empty[st]);
+            if (!has_next) umma_commit(q_empty_i);  // last S MMAs of this item issued
+          }
+          st_prev = st;
           st = st_next;
           ph = ph_next;
         }
+        if (act1) {  // drain: PV1(n-1)
+          mbar_wait(&p_full[1], p_cnt[1] & 1);
+          ++p_cnt[1];
+          tc_fence_after();
+          issue_pv(1, st_prev, tail_cols, n_kv == 1);
+          umma_commit(&o_full[1]);
+          umma_commit(&v_empty[st_prev]);
+        }
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // ===================== softmax groups (thread == query row of tile g) =====================
-    const int g = (warp - 2) >> 2;          // 0: warps 2-5, 1: warps 6-9
+    const int g = (warp - 4) >> 2;          // 0: warps 4-7, 1: warps 8-11
     const int quad = warp & 3;              // TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
@@ -245,77 +275,132 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t t_o = tmem_base + lane_addr + o_col(g);
     const float c = args.scale_log2;
     uint32_t s_cnt = 0, o_cnt = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int bh = item / n_pairs, pair = item % n_pairs;
-      const int q0 = pair * 2 * A2_BQ + g * A2_BQ;
+      const int q0 = q_off + pair * 2 * A2_BQ + g * A2_BQ;
       if (q0 >= seq) continue;  // inactive second tile: the whole group skips this item
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < n_kv; ++j) {
         const int kv0 = j * A2_BKV;
         const bool last = (j == n_kv - 1);
-        const int nchunks = last ? (tail_cols + 31) / 32 : A2_BKV / 32;
+        if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 4 + 0);
         mbar_wait(&s_full[g], s_cnt & 1);
+        if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 4 + 1);
         ++s_cnt;
         tc_fence_after();
-        // pass 1: row maximum over the valid keys
-        float mx = -INFINITY;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_s + ch * 32, v);
+        if (!last || tail_keys == A2_BKV) {
+          // ---------- full tile: the whole S row lives in registers (one TMEM read, no masking) ----------
+          uint32_t sv[128];
+          tmem_ld_32x32b_x32p(t_s + 0, sv + 0);
+          tmem_ld_32x32b_x32p(t_s + 32, sv + 32);
+          tmem_ld_32x32b_x32p(t_s + 64, sv + 64);
+          tmem_ld_32x32b_x32p(t_s + 96, sv + 96);
           tmem_wait_ld();
+          if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 4 + 2);
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float s = __uint_as_float(v[i]);
-            if (last && kv0 + ch * 32 + i >= seq) s = -INFINITY;
-            mx = fmaxf(mx, s);
+          for (int i = 0; i < 128; i += 8) {
+            mx0 = fmax3(mx0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+            mx2 = fmax3(mx2, __uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5]));
+            mx3 = fmax3(mx3, __uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7]));
           }
-        }
-        // lazy maximum update: only move (and rescale O) when the maximum grew by more than 2^8
-        float alpha = 1.0f;
-        if (j == 0) {
-          m_run = mx;
-        } else if ((mx - m_run) * c > 8.0f) {
-          alpha = exp2f((m_run - mx) * c);
-          m_run = mx;
-        }
-        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll
-          for (int ch = 0; ch < HD / 32; ++ch) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(t_o + ch * 32, v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st_32x32b_x32(t_o + ch * 32, v);
+          const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+          float alpha = 1.0f;
+          if (j == 0) {
+            m_run = mx;
+          } else if ((mx - m_run) * c > 8.0f) {  // lazy maximum: move only when it grew by more than 2^8
+            alpha = ex2_approx((m_run - mx) * c);
+            m_run = mx;
           }
           l_run *= alpha;
-        }
-        const float mc = m_run * c;
-        // pass 2: P = exp2(s*c - m*c) -> bf16 -> TMEM (aliasing S), row sum
-        float psum = 0.f;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_s + ch * 32, v);
-          tmem_wait_ld();
-          uint32_t w[16];
+          const float nmc = -m_run * c;
+          float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), c, -mc));
-            float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
-            if (last) {
+          for (int i = 0; i < 64; i += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), c, nmc));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), c, nmc));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 2]), c, nmc));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 3]), c, nmc));
+            ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
+            sv[i] = pack_bf16x2(p0, p1);       // in place: word i is written after elements 2i, 2i+1 were consumed
+            sv[i + 1] = pack_bf16x2(p2, p3);
+          }
+          tmem_st_32x32b_x32p(t_s + 0, sv + 0);
+          tmem_st_32x32b_x32p(t_s + 32, sv + 32);
+          l_run += (ps0 + ps1) + (ps2 + ps3);
+          // O rescale, deferred until the S registers are dead (PV_g(j) is only issued after this group's arrival)
+          if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+            for (int ch = 0; ch < HD / 32; ++ch) {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(t_o + ch * 32, v);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st_32x32b_x32(t_o + ch * 32, v);
+            }
+          }
+        } else {
+          // ---------- trimmed last tile: chunked, masked, two passes over TMEM ----------
+          const int nchunks = (tail_cols + 31) / 32;
+          float mx = -INFINITY;
+          for (int ch = 0; ch < nchunks; ++ch) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_s + ch * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float sc = __uint_as_float(v[i]);
+              if (kv0 + ch * 32 + i >= seq) sc = -INFINITY;
+              mx = fmaxf(mx, sc);
+            }
+          }
+          float alpha = 1.0f;
+          if (j == 0) {
+            m_run = mx;
+          } else if ((mx - m_run) * c > 8.0f) {
+            alpha = ex2_approx((m_run - mx) * c);
+            m_run = mx;
+          }
+          if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+            for (int ch = 0; ch < HD / 32; ++ch) {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(t_o + ch * 32, v);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st_32x32b_x32(t_o + ch * 32, v);
+            }
+            l_run *= alpha;
+          }
+          const float nmc = -m_run * c;
+          float psum = 0.f;
+          for (int ch = 0; ch < nchunks; ++ch) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_s + ch * 32, v);
+            tmem_wait_ld();
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, nmc));
+              float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, nmc));
               if (kv0 + ch * 32 + 2 * i >= seq) p0 = 0.f;
               if (kv0 + ch * 32 + 2 * i + 1 >= seq) p1 = 0.f;
+              psum += p0 + p1;
+              w[i] = pack_bf16x2(p0, p1);
             }
-            psum += p0 + p1;
-            w[i] = pack_bf16x2(p0, p1);
+            tmem_st_32x32b_x16(t_s + ch * 16, w);
           }
-          tmem_st_32x32b_x16(t_s + ch * 16, w);
+          l_run += psum;
         }
-        l_run += psum;
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g]);
+        if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 4 + 3);
       }
       // ---- epilogue: O / l -> bf16, token-major ----
       mbar_wait(&o_full[g], o_cnt & 1);
@@ -357,10 +442,12 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 static int g_att2_sms = 0;
+static long long* g_att2_trace = nullptr;
+void attention_tc2_set_trace(long long* dev_buf) { g_att2_trace = dev_buf; }
 
 template <int HD>
 static cudaError_t launch_att2(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int seq, int seq_pad,
-                               float scale, cudaStream_t s) {
+                               float scale, int q_off, cudaStream_t s) {
   using Cfg = Att2Cfg<HD>;
   const int BH = L * heads;
   CUtensorMap tq, tk, tv;
@@ -379,19 +466,94 @@ static cudaError_t launch_att2(const bf16* Q, const bf16* K, const bf16* Vt, bf1
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_att2_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int n_qt = (seq + A2_BQ - 1) / A2_BQ;
+  const int n_qt = (seq - q_off + A2_BQ - 1) / A2_BQ;
   const int n_items = BH * ((n_qt + 1) / 2);
   const int grid = n_items < g_att2_sms ? n_items : g_att2_sms;
-  Att2Args a{O, heads, seq, seq_pad, BH, scale * 1.4426950408889634f};
+  Att2Args a{O, heads, seq, seq_pad, BH, q_off, scale * 1.4426950408889634f, g_att2_trace};
   kern<<<grid, A2_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tk, tv, a);
+  return cudaGetLastError();
+}
+
+// Rows [0, nrows) of every sequence on CUDA cores: one warp per (bh, row).  Used for the few tokens (DINOv2: cls + 4
+// registers) that would otherwise cost a whole extra 128-row query tile.
+template <int HD>
+__global__ void __launch_bounds__(128) attention_prefix_rows_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K,
+                                                                    const bf16* __restrict__ Vt, bf16* __restrict__ O, int heads,
+                                                                    int seq, int seq_pad, int nrows, int total, float scale_log2) {
+  extern __shared__ float sp[];  // [4 warps][seq]
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= total) return;
+  const int bh = w / nrows, row = w % nrows;
+  float* p = sp + (threadIdx.x >> 5) * seq;
+  const bf16* q = Q + (static_cast<long long>(bh) * seq_pad + row) * HD;
+  float qf[HD / 32];
+#pragma unroll
+  for (int i = 0; i < HD / 32; ++i) qf[i] = __bfloat162float(q[lane + 32 * i]);
+  // scores: lanes split the head dim, keys serial (HD is small); warp-reduce each score
+  float mx = -INFINITY;
+  for (int key = 0; key < seq; ++key) {
+    const bf16* kr = K + (static_cast<long long>(bh) * seq_pad + key) * HD;
+    float sacc = 0.f;
+#pragma unroll
+    for (int i = 0; i < HD / 32; ++i) sacc = fmaf(qf[i], __bfloat162float(kr[lane + 32 * i]), sacc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+    if (lane == 0) p[key] = sacc;
+    mx = fmaxf(mx, sacc);
+  }
+  __syncwarp();
+  float sum = 0.f;
+  for (int key = lane; key < seq; key += 32) {
+    const float e = exp2f((p[key] - mx) * scale_log2);
+    p[key] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncwarp();
+  const float inv = 1.0f / sum;
+  const int l_idx = bh / heads, head = bh % heads;
+  bf16* dst = O + (static_cast<long long>(l_idx) * seq + row) * (heads * HD) + head * HD;
+#pragma unroll
+  for (int i = 0; i < HD / 32; ++i) {
+    const int dcol = lane + 32 * i;
+    const bf16* vr = Vt + (static_cast<long long>(bh) * HD + dcol) * seq_pad;
+    float acc = 0.f;
+    for (int key = 0; key < seq; ++key) acc = fmaf(__bfloat162float(__float2bfloat16_rn(p[key])), __bfloat162float(vr[key]), acc);
+    dst[dcol] = __float2bfloat16_rn(acc * inv);
+  }
+}
+
+template <int HD>
+static cudaError_t launch_prefix(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int seq, int seq_pad,
+                                 int nrows, float scale, cudaStream_t s) {
+  const int total = L * heads * nrows;
+  const size_t smem = 4 * static_cast<size_t>(seq) * sizeof(float);
+  auto kern = attention_prefix_rows_kernel<HD>;
+  if (smem > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+  }
+  kern<<<(total + 3) / 4, 128, smem, s>>>(Q, K, Vt, O, heads, seq, seq_pad, nrows, total, scale * 1.4426950408889634f);
   return cudaGetLastError();
 }
 
 cudaError_t attention_tc2(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int head_dim, int seq,
                           int seq_pad, float scale, cudaStream_t s) {
   if (seq_pad % 128 != 0 || seq > seq_pad || seq <= 0) return cudaErrorInvalidValue;
-  if (head_dim == 96) return launch_att2<96>(Q, K, Vt, O, L, heads, seq, seq_pad, scale, s);
-  if (head_dim == 64) return launch_att2<64>(Q, K, Vt, O, L, heads, seq, seq_pad, scale, s);
+  // a handful of rows beyond a multiple of 128 (DINOv2: 5 + 256) would cost a whole extra query tile: peel them off
+  const int rem = seq % A2_BQ;
+  const int q_off = (rem > 0 && rem <= 8 && seq > A2_BQ) ? rem : 0;
+  cudaError_t err;
+  if (head_dim == 96) {
+    if (q_off && (err = launch_prefix<96>(Q, K, Vt, O, L, heads, seq, seq_pad, q_off, scale, s)) != cudaSuccess) return err;
+    return launch_att2<96>(Q, K, Vt, O, L, heads, seq, seq_pad, scale, q_off, s);
+  }
+  if (head_dim == 64) {
+    if (q_off && (err = launch_prefix<64>(Q, K, Vt, O, L, heads, seq, seq_pad, q_off, scale, s)) != cudaSuccess) return err;
+    return launch_att2<64>(Q, K, Vt, O, L, heads, seq, seq_pad, scale, q_off, s);
+  }
   return cudaErrorInvalidValue;
 }
 

@@ -626,3 +626,10 @@ extern "C" int bd_profile_read(bd_handle e, double* ms_out, int64_t* count_out, 
   if (reset) for (int i = 0; i < BD_PROF_NCAT; ++i) { e->cat_ms[i] = 0; e->cat_n[i] = 0; }
   return BD_OK;
 }
+
+// debug aid: per-role clock stamps of the v2 attention kernel (CTA 0); dev_buf must hold 3*512 int64, nullptr disables
+namespace bd { void attention_tc2_set_trace(long long* dev_buf); }
+extern "C" int bd_debug_attention_trace(void* dev_buf) {
+  bd::attention_tc2_set_trace(reinterpret_cast<long long*>(dev_buf));
+  return BD_OK;
+}

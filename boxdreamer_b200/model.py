@@ -75,7 +75,7 @@ class Engine:
             raise _lib.BoxDreamerLibError("boxdreamer_b200 needs a CUDA device: the hot path has no CPU fallback")
         self.lib = _lib.load()
         if attn_variant is None:
-            attn_variant = int(os.environ.get("BOXDREAMER_B200_ATTN_VARIANT", "1"))
+            attn_variant = int(os.environ.get("BOXDREAMER_B200_ATTN_VARIANT", "2"))
         self.cfg = _lib.BdConfig(img_size, patch, d_model, dec_layers, dec_heads, dino_layers, dino_heads,
                                  dino_registers, 37, precision, attn_variant, max_batch, max_views)
         self.handle = C.c_void_p()

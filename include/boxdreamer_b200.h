@@ -148,6 +148,9 @@ int bd_profile_enable(bd_handle h, int32_t on);
 /* synchronises, then returns accumulated milliseconds and launch counts per BD_PROF_* category */
 int bd_profile_read(bd_handle h, double* ms_out, int64_t* count_out, int32_t reset);
 
+/* debug aid: clock64 stamps of the persistent attention kernel's roles (CTA 0) into dev_buf[3*512] (int64); NULL disables */
+int bd_debug_attention_trace(void* dev_buf);
+
 #ifdef __cplusplus
 }
 #endif

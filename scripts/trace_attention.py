@@ -1,0 +1,30 @@
+"""Debug aid: role timeline of the persistent attention kernel (CTA 0, first item)."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from boxdreamer_b200 import _lib
+lib = _lib.load()
+L, heads, hd, seq = 64, 8, 96, 1536
+seq_pad = (seq + 127) // 128 * 128
+Q = torch.randn(L * heads, seq_pad, hd, device="cuda").to(torch.bfloat16)
+K = torch.randn_like(Q)
+Vt = torch.randn(L * heads, hd, seq_pad, device="cuda").to(torch.bfloat16)
+O = torch.empty(L * seq, heads * hd, device="cuda", dtype=torch.bfloat16)
+def run():
+    _lib.check(lib.bd_attention(_lib.ptr(Q), _lib.ptr(K), _lib.ptr(Vt), _lib.ptr(O), L, heads, hd, seq, seq_pad, hd ** -0.5, 1, 2, None))
+for _ in range(3):
+    run()
+torch.cuda.synchronize()
+tr = torch.zeros(3 * 512, dtype=torch.int64, device="cuda")
+lib.bd_debug_attention_trace(_lib.ptr(tr))
+run()
+torch.cuda.synchronize()
+lib.bd_debug_attention_trace(None)
+t = tr.cpu().view(3, 128, 4)
+t0 = int(t[t > 0].min())
+n_kv = 12
+print("item j | MMA: waitP0 start/end, waitP1 start/end | SM0: wait start, S seen, ld done, arrive | SM1: ...   (cycles since first stamp)")
+for idx in range(2 * n_kv + 4):
+    row = [int(x) - t0 if int(x) > 0 else -1 for x in t[:, idx, :].reshape(-1)]
+    print(f"{idx // n_kv:2d} {idx % n_kv:2d} | " + " ".join(f"{v:7d}" for v in row[0:4]) + " | " + " ".join(f"{v:7d}" for v in row[4:8]) + " | " +
+          " ".join(f"{v:7d}" for v in row[8:12]))

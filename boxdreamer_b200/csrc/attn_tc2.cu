@@ -11,6 +11,8 @@
 //     exact because the same maximum scales P and the row sum;
 //   * the last K/V tile is trimmed to the next multiple of 16 keys (runtime UMMA N / K), which removes most of the
 //     padding waste of short sequences (DINOv2: 261 keys = 2 tiles + 16 keys instead of 3 tiles).
+#include <stdlib.h>
+
 #include "bd_internal.h"
 #include "common.cuh"
 
@@ -474,68 +476,176 @@ static cudaError_t launch_att2(const bf16* Q, const bf16* K, const bf16* Vt, bf1
   return cudaGetLastError();
 }
 
-// Rows [0, nrows) of every sequence on CUDA cores: one warp per (bh, row).  Used for the few tokens (DINOv2: cls + 4
-// registers) that would otherwise cost a whole extra 128-row query tile.
-template <int HD>
-__global__ void __launch_bounds__(128) attention_prefix_rows_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K,
+// Rows [0, nrows) of every sequence on CUDA cores: one CTA per (l, h).  K and V^T are streamed once with 16-byte
+// loads (no staging); every thread folds its 8 keys / 8 dims into all nrows rows at once.  Used for the few tokens
+// (DINOv2: cls + 4 registers) that would otherwise cost a whole extra 128-row query tile.
+static constexpr int PFX_MAXSEQ = 640;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+template <int HD, int NR>
+__global__ void __launch_bounds__(256, 4) attention_prefix_rows_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K,
                                                                     const bf16* __restrict__ Vt, bf16* __restrict__ O, int heads,
-                                                                    int seq, int seq_pad, int nrows, int total, float scale_log2) {
-  extern __shared__ float sp[];  // [4 warps][seq]
-  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (w >= total) return;
-  const int bh = w / nrows, row = w % nrows;
-  float* p = sp + (threadIdx.x >> 5) * seq;
-  const bf16* q = Q + (static_cast<long long>(bh) * seq_pad + row) * HD;
-  float qf[HD / 32];
-#pragma unroll
-  for (int i = 0; i < HD / 32; ++i) qf[i] = __bfloat162float(q[lane + 32 * i]);
-  // scores: lanes split the head dim, keys serial (HD is small); warp-reduce each score
-  float mx = -INFINITY;
-  for (int key = 0; key < seq; ++key) {
-    const bf16* kr = K + (static_cast<long long>(bh) * seq_pad + key) * HD;
-    float sacc = 0.f;
-#pragma unroll
-    for (int i = 0; i < HD / 32; ++i) sacc = fmaf(qf[i], __bfloat162float(kr[lane + 32 * i]), sacc);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-    if (lane == 0) p[key] = sacc;
-    mx = fmaxf(mx, sacc);
+                                                                    int seq, int seq_pad, float scale_log2) {
+  constexpr int nrows = NR;
+  __shared__ float sQ[NR][HD];
+  __shared__ __align__(16) float sS[NR][PFX_MAXSEQ + 8];
+  __shared__ float sO[NR][HD];
+  __shared__ float sInv[NR];
+  const int bh = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bf16* Kb = K + static_cast<long long>(bh) * seq_pad * HD;
+  const bf16* Vb = Vt + static_cast<long long>(bh) * HD * seq_pad;
+  const int nch_k = (seq + 7) / 8;  // 8-key chunks
+  for (int i = tid; i < nrows * HD; i += 256) {
+    sQ[i / HD][i % HD] = __bfloat162float(Q[(static_cast<long long>(bh) * seq_pad + i / HD) * HD + (i % HD)]);
+    sO[i / HD][i % HD] = 0.f;
   }
-  __syncwarp();
-  float sum = 0.f;
-  for (int key = lane; key < seq; key += 32) {
-    const float e = exp2f((p[key] - mx) * scale_log2);
-    p[key] = e;
-    sum += e;
-  }
+  for (int i = tid; i < nrows * (PFX_MAXSEQ + 8); i += 256) (&sS[0][0])[i] = 0.f;
+  __syncthreads();
+  // scores: work item = (key, 8-dim chunk); the CH chunks of a key sit in adjacent lanes
+  constexpr int CH = HD / 8;
+  const int n_items = (seq * CH + 255) / 256 * 256;  // whole warps take part in the shuffles
+  float qreg[NR][8];
+  {
+    const int chq = tid % CH;  // for CH == 8 every work item of this thread has the same chunk index
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  __syncwarp();
-  const float inv = 1.0f / sum;
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qreg[r][i] = (r < nrows) ? sQ[r][chq * 8 + i] : 0.f;
+  }
+  for (int w0 = tid; w0 < n_items; w0 += 256 * 4) {   // 4 independent 16-byte loads in flight per thread
+    uint4 u[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int w = w0 + b * 256;
+      const int key = w / CH, ch = w % CH;
+      u[b] = make_uint4(0u, 0u, 0u, 0u);
+      if (w < n_items && key < seq) u[b] = __ldg(reinterpret_cast<const uint4*>(Kb + static_cast<long long>(key) * HD + ch * 8));
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int w = w0 + b * 256;
+      if (w >= n_items) break;  // warp-uniform: n_items is a multiple of 256
+      const int key = w / CH, ch = w % CH;
+      float kf[8];
+      unpack8(u[b], kf);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        if (r >= nrows) break;
+        float acc = 0.f;
+        if constexpr (CH == 8) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc = fmaf(qreg[r][i], kf[i], acc);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+          if (ch == 0 && key < seq) sS[r][key] = acc;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc = fmaf(sQ[r][ch * 8 + i], kf[i], acc);
+          if (key < seq) atomicAdd(&sS[r][key], acc);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp < nrows) {
+    float* p = sS[warp];
+    float mx = -INFINITY;
+    for (int key = lane; key < seq; key += 32) mx = fmaxf(mx, p[key]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int key = lane; key < nch_k * 8; key += 32) {
+      float e = 0.f;
+      if (key < seq) {
+        e = exp2f((p[key] - mx) * scale_log2);
+        sum += e;
+        e = __bfloat162float(__float2bfloat16_rn(e));  // P is bf16 on the tensor path too
+      }
+      p[key] = e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) sInv[warp] = 1.0f / sum;
+  }
+  __syncthreads();
+  // P V: 4 lanes per output dim split the 8-key chunks, registers accumulate all rows, one shuffle reduction at the end
+  for (int d0 = 0; d0 < HD; d0 += 64) {
+    const int dcol = d0 + (tid >> 2), part = tid & 3;
+    float acc[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) acc[r] = 0.f;
+    if (dcol < HD) {
+      for (int c0 = part; c0 < nch_k; c0 += 16) {   // 4 independent 16-byte loads in flight per thread
+        uint4 u[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int c = c0 + 4 * b;
+          u[b] = make_uint4(0u, 0u, 0u, 0u);
+          if (c < nch_k) u[b] = __ldg(reinterpret_cast<const uint4*>(Vb + static_cast<long long>(dcol) * seq_pad + c * 8));
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int c = c0 + 4 * b;
+          if (c < nch_k) {
+            float vf[8];
+            unpack8(u[b], vf);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              if (r < nrows) {
+                const float4 p0 = *reinterpret_cast<const float4*>(&sS[r][c * 8]);
+                const float4 p1 = *reinterpret_cast<const float4*>(&sS[r][c * 8 + 4]);
+                acc[r] = fmaf(p0.x, vf[0], acc[r]); acc[r] = fmaf(p0.y, vf[1], acc[r]);
+                acc[r] = fmaf(p0.z, vf[2], acc[r]); acc[r] = fmaf(p0.w, vf[3], acc[r]);
+                acc[r] = fmaf(p1.x, vf[4], acc[r]); acc[r] = fmaf(p1.y, vf[5], acc[r]);
+                acc[r] = fmaf(p1.z, vf[6], acc[r]); acc[r] = fmaf(p1.w, vf[7], acc[r]);
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
+      acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 2);
+      if (part == 0 && dcol < HD && r < nrows) sO[r][dcol] = acc[r];
+    }
+  }
+  __syncthreads();
   const int l_idx = bh / heads, head = bh % heads;
-  bf16* dst = O + (static_cast<long long>(l_idx) * seq + row) * (heads * HD) + head * HD;
-#pragma unroll
-  for (int i = 0; i < HD / 32; ++i) {
-    const int dcol = lane + 32 * i;
-    const bf16* vr = Vt + (static_cast<long long>(bh) * HD + dcol) * seq_pad;
-    float acc = 0.f;
-    for (int key = 0; key < seq; ++key) acc = fmaf(__bfloat162float(__float2bfloat16_rn(p[key])), __bfloat162float(vr[key]), acc);
-    dst[dcol] = __float2bfloat16_rn(acc * inv);
+  for (int i = tid; i < nrows * HD; i += 256) {
+    const int r = i / HD, dcol = i % HD;
+    O[(static_cast<long long>(l_idx) * seq + r) * (heads * HD) + head * HD + dcol] = __float2bfloat16_rn(sO[r][dcol] * sInv[r]);
   }
 }
 
 template <int HD>
 static cudaError_t launch_prefix(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int seq, int seq_pad,
                                  int nrows, float scale, cudaStream_t s) {
-  const int total = L * heads * nrows;
-  const size_t smem = 4 * static_cast<size_t>(seq) * sizeof(float);
-  auto kern = attention_prefix_rows_kernel<HD>;
-  if (smem > 48 * 1024) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (err != cudaSuccess) return err;
+  if (nrows > 8 || nrows < 1 || seq > PFX_MAXSEQ) return cudaErrorInvalidValue;
+  const float sl = scale * 1.4426950408889634f;
+  const int grid = L * heads;
+  switch (nrows) {
+    case 1: attention_prefix_rows_kernel<HD, 1><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
+    case 2: attention_prefix_rows_kernel<HD, 2><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
+    case 3: attention_prefix_rows_kernel<HD, 3><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
+    case 4: attention_prefix_rows_kernel<HD, 4><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
+    case 5: attention_prefix_rows_kernel<HD, 5><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
+    case 6: attention_prefix_rows_kernel<HD, 6><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
+    case 7: attention_prefix_rows_kernel<HD, 7><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
+    default: attention_prefix_rows_kernel<HD, 8><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
   }
-  kern<<<(total + 3) / 4, 128, smem, s>>>(Q, K, Vt, O, heads, seq, seq_pad, nrows, total, scale * 1.4426950408889634f);
   return cudaGetLastError();
 }
 
@@ -544,8 +654,19 @@ cudaError_t attention_tc2(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O,
   if (seq_pad % 128 != 0 || seq > seq_pad || seq <= 0) return cudaErrorInvalidValue;
   // a handful of rows beyond a multiple of 128 (DINOv2: 5 + 256) would cost a whole extra query tile: peel them off
   const int rem = seq % A2_BQ;
-  const int q_off = (rem > 0 && rem <= 8 && seq > A2_BQ) ? rem : 0;
+  static const bool no_peel = getenv("BD_ATT2_NOPEEL") != nullptr;  // debug switch
+  const int q_off = (!no_peel && rem > 0 && rem <= 8 && seq > A2_BQ && seq <= 640) ? rem : 0;
   cudaError_t err;
+  static const char* only = getenv("BD_ATT2_ONLY");  // debug switch: "prefix" or "main"
+  if (only && only[0] == 'p') {
+    if (!q_off) return cudaSuccess;
+    return head_dim == 96 ? launch_prefix<96>(Q, K, Vt, O, L, heads, seq, seq_pad, q_off, scale, s)
+                          : launch_prefix<64>(Q, K, Vt, O, L, heads, seq, seq_pad, q_off, scale, s);
+  }
+  if (only && only[0] == 'm') {
+    return head_dim == 96 ? launch_att2<96>(Q, K, Vt, O, L, heads, seq, seq_pad, scale, q_off, s)
+                          : launch_att2<64>(Q, K, Vt, O, L, heads, seq, seq_pad, scale, q_off, s);
+  }
   if (head_dim == 96) {
     if (q_off && (err = launch_prefix<96>(Q, K, Vt, O, L, heads, seq, seq_pad, q_off, scale, s)) != cudaSuccess) return err;
     return launch_att2<96>(Q, K, Vt, O, L, heads, seq, seq_pad, scale, q_off, s);

@@ -139,6 +139,64 @@ BD_HD void jacobi_eig_sym12(double* A, double* V) {
   }
 }
 
+// Eigenvector of the smallest eigenvalue of a symmetric positive semi-definite 12x12 (row-major, flat) by inverse
+// iteration on the Cholesky factor of (A + eps*tr*I): ~25x less work than the full Jacobi decomposition and the
+// serial latency that dominates one-thread-per-query PnP.  Returns false when the factorisation breaks down (the
+// caller then falls back to Jacobi).  L overwrites the lower triangle of A.
+BD_HD bool smallest_eigvec_sym12(double* A, double* x) {
+  double tr = 0.0;
+  for (int i = 0; i < 12; ++i) tr += A[i * 13];
+  if (!(tr > 0.0)) return false;
+  const double shift = 1e-10 * tr;
+  for (int j = 0; j < 12; ++j) {
+    double d = A[j * 13] + shift;
+#pragma unroll 1
+    for (int k = 0; k < j; ++k) d -= A[j * 12 + k] * A[j * 12 + k];
+    if (!(d > 1e-300)) return false;
+    d = sqrt(d);
+    A[j * 13] = d;
+#pragma unroll 1
+    for (int i = j + 1; i < 12; ++i) {
+      double v = A[i * 12 + j];
+#pragma unroll 1
+      for (int k = 0; k < j; ++k) v -= A[i * 12 + k] * A[j * 12 + k];
+      A[i * 12 + j] = v / d;
+    }
+  }
+  for (int i = 0; i < 12; ++i) x[i] = 1.0 / (1.0 + i);
+  double y[12];
+  for (int it = 0; it < 60; ++it) {
+#pragma unroll 1
+    for (int i = 0; i < 12; ++i) {
+      double v = x[i];
+#pragma unroll 1
+      for (int k = 0; k < i; ++k) v -= A[i * 12 + k] * y[k];
+      y[i] = v / A[i * 13];
+    }
+#pragma unroll 1
+    for (int i = 11; i >= 0; --i) {
+      double v = y[i];
+#pragma unroll 1
+      for (int k = i + 1; k < 12; ++k) v -= A[k * 12 + i] * y[k];
+      y[i] = v / A[i * 13];
+    }
+    double n = 0.0;
+    for (int i = 0; i < 12; ++i) n += y[i] * y[i];
+    n = sqrt(n);
+    if (!(n > 0.0) || !isfinite(n)) return false;
+    double diff = 0.0, dot = 0.0;
+    for (int i = 0; i < 12; ++i) dot += x[i] * y[i];
+    const double sgn = dot < 0.0 ? -1.0 : 1.0;
+    for (int i = 0; i < 12; ++i) {
+      const double xn = sgn * y[i] / n;
+      diff += (xn - x[i]) * (xn - x[i]);
+      x[i] = xn;
+    }
+    if (diff < 1e-26 && it >= 2) break;
+  }
+  return true;
+}
+
 BD_HD __forceinline__ double det3(const double (&R)[3][3]) {
   return R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
          R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
@@ -250,14 +308,25 @@ BD_HD void pnp_dlt_init(const PnpProblem& pb, double (&R)[3][3], double (&t)[3])
     for (int a = 0; a < 12; ++a)
       for (int b = 0; b < 12; ++b) A[a * 12 + b] += r1[a] * r1[b] + r2[a] * r2[b];
   }
-  jacobi_eig_sym12(A, V);
-  int kmin = 0;
-  for (int k = 1; k < 12; ++k)
-    if (A[k * 13] < A[kmin * 13]) kmin = k;
   double Rd[3][3], td[3];
-  for (int a = 0; a < 3; ++a) {
-    for (int b = 0; b < 3; ++b) Rd[a][b] = V[(a * 4 + b) * 12 + kmin];
-    td[a] = V[(a * 4 + 3) * 12 + kmin];
+  {
+    double B[144], ev[12];
+    for (int i = 0; i < 144; ++i) B[i] = A[i];
+    if (smallest_eigvec_sym12(B, ev)) {
+      for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) Rd[a][b] = ev[a * 4 + b];
+        td[a] = ev[a * 4 + 3];
+      }
+    } else {
+      jacobi_eig_sym12(A, V);
+      int kmin = 0;
+      for (int k = 1; k < 12; ++k)
+        if (A[k * 13] < A[kmin * 13]) kmin = k;
+      for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) Rd[a][b] = V[(a * 4 + b) * 12 + kmin];
+        td[a] = V[(a * 4 + 3) * 12 + kmin];
+      }
+    }
   }
   if (det3(Rd) < 0.0) {
     for (int a = 0; a < 3; ++a) {

@@ -2,6 +2,7 @@
 // inference path (DINOv2 ViT-B/14-reg -> BETR decoder -> heat maps -> top-20 corners -> PnP) on one stream.
 // See include/boxdreamer_b200.h for the contract and the reference call sites each entry replaces.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -67,6 +68,8 @@ struct bd_engine {
   void* in_images = nullptr; void* in_bbox = nullptr;  // device staging for bd_forward_host
   float* pos_dec = nullptr;  // f32 [P, d] 2-D sincos table
   cudaStream_t host_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[8] = {nullptr};
   // instrumentation: kernel launch counter and optional per-category CUDA-event timing
   long long launches = 0;
   bool profile = false;
@@ -205,6 +208,8 @@ extern "C" int bd_destroy(bd_handle e) {
   cudaDeviceSynchronize();
   for (void* p : e->allocs) cudaFree(p);
   if (e->host_stream) cudaStreamDestroy(e->host_stream);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  for (int i = 0; i < 8; ++i) if (e->copy_ev[i]) cudaEventDestroy(e->copy_ev[i]);
   delete e;
   return BD_OK;
 }
@@ -470,7 +475,7 @@ extern "C" int bd_corners_topk(bd_handle e, const float* heat, float* corners_px
 }
 
 static PnpOpts to_opts(const bd_pnp_opts* o) {
-  PnpOpts p{0, 0, 1.0f, 0u, 100};
+  PnpOpts p{0, 0, 1.0f, 0u, 30};
   if (o) { p.mode = o->mode; p.n_hyp = o->n_hyp; p.thr_px = o->thr_px; p.seed = o->seed; p.max_iter = o->max_iter; }
   return p;
 }
@@ -522,15 +527,39 @@ extern "C" int bd_forward_host(bd_handle e, const void* images_host, const void*
     CK(cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking));
   }
   cudaStream_t s = e->host_stream;
-  const size_t L = static_cast<size_t>(B) * T;
-  CK(cudaMemcpyAsync(e->in_images, images_host, L * 3 * SS * es, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(e->in_bbox, bbox_feat_host, L * 8 * SS * es, cudaMemcpyHostToDevice, s));
+  if (!e->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&e->copy_ev[i], cudaEventDisableTiming));
+  }
+  // The batch is processed in chunks of whole queries: chunk i+1's H2D (copy stream) overlaps chunk i's compute.
+  int nchunk = B >= 32 ? 2 : 1;
+  if (const char* ev = getenv("BOXDREAMER_B200_HOST_CHUNKS")) nchunk = atoi(ev);
+  if (nchunk < 1) nchunk = 1;
+  if (nchunk > 8) nchunk = 8;
+  if (nchunk > B) nchunk = B;
   CK(cudaMemcpyAsync(e->qidx, query_idx_host, static_cast<size_t>(B) * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(e->bbox3d_q, bbox3d_q_host, static_cast<size_t>(B) * 24 * 4, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(e->K_q, K_q_host, static_cast<size_t>(B) * 9 * 4, cudaMemcpyHostToDevice, s));
-  int r = bd_forward(e, e->in_images, e->in_bbox, in_dtype, e->qidx, e->bbox3d_q, e->K_q, e->heat, e->corners_px, e->corners_norm,
-                     e->poses, opts, B, T, s);
-  if (r != BD_OK) return r;
+  const size_t img_q = static_cast<size_t>(T) * 3 * SS * es, box_q = static_cast<size_t>(T) * 8 * SS * es;  // bytes per query
+  int b0s[9];
+  for (int c = 0; c <= nchunk; ++c) b0s[c] = static_cast<int>(static_cast<long long>(B) * c / nchunk);
+  for (int c = 0; c < nchunk; ++c) {
+    const int b0 = b0s[c], nb = b0s[c + 1] - b0s[c];
+    CK(cudaMemcpyAsync(static_cast<char*>(e->in_images) + b0 * img_q, static_cast<const char*>(images_host) + b0 * img_q, nb * img_q,
+                       cudaMemcpyHostToDevice, e->copy_stream));
+    CK(cudaMemcpyAsync(static_cast<char*>(e->in_bbox) + b0 * box_q, static_cast<const char*>(bbox_feat_host) + b0 * box_q, nb * box_q,
+                       cudaMemcpyHostToDevice, e->copy_stream));
+    CK(cudaEventRecord(e->copy_ev[c], e->copy_stream));
+  }
+  for (int c = 0; c < nchunk; ++c) {
+    const int b0 = b0s[c], nb = b0s[c + 1] - b0s[c];
+    if (nb <= 0) continue;
+    CK(cudaStreamWaitEvent(s, e->copy_ev[c], 0));
+    int r = bd_forward(e, static_cast<char*>(e->in_images) + b0 * img_q, static_cast<char*>(e->in_bbox) + b0 * box_q, in_dtype,
+                       e->qidx + b0, e->bbox3d_q + b0 * 24, e->K_q + b0 * 9, e->heat + static_cast<size_t>(b0) * 8 * SS,
+                       e->corners_px + b0 * 16, e->corners_norm + b0 * 16, e->poses + b0 * 16, opts, nb, T, s);
+    if (r != BD_OK) return r;
+  }
   CK(cudaMemcpyAsync(corners_px_host, e->corners_px, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(corners_norm_host, e->corners_norm, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(poses_out_host, e->poses, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToHost, s));

@@ -445,7 +445,7 @@ cudaError_t pnp_solve(const float* corners_px, const float* bbox3d, const float*
   if (B <= 0) return cudaSuccess;
   if (n_pts < 6 || n_pts > PNP_MAXPTS) return cudaErrorInvalidValue;
   if (o.mode != 0) return cudaErrorNotSupported;
-  const int max_iter = o.max_iter > 0 ? o.max_iter : 100;
+  const int max_iter = o.max_iter > 0 ? o.max_iter : 30;  // converged within 15 on realistic corners; OpenCV caps its LM at 20
   pnp_iterative_kernel<<<(B + 63) / 64, 64, 0, s>>>(corners_px, bbox3d, K, poses, B, n_pts, max_iter);
   return cudaGetLastError();
 }

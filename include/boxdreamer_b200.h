@@ -94,7 +94,7 @@ typedef struct {
   int32_t n_hyp;     /* mode 1: hypotheses per query                   */
   float thr_px;      /* mode 1: inlier threshold in pixels             */
   uint32_t seed;     /* mode 1                                         */
-  int32_t max_iter;  /* LM iteration cap (0 -> 100)                    */
+  int32_t max_iter;  /* LM iteration cap (0 -> 30)                     */
 } bd_pnp_opts;
 
 /* recover_pose_from_bb8 (utils/box_utils.py:113-199): corners_px [B,n,2], bbox3d [B,n,3], K [B,3,3] (fp32)

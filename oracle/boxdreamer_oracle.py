@@ -293,9 +293,10 @@ def pnp_dlt_init(X: np.ndarray, uv: np.ndarray, K: np.ndarray):
 
 
 def pnp_lm(X: np.ndarray, uv: np.ndarray, K: np.ndarray, R: np.ndarray, t: np.ndarray,
-           max_iter: int = 100, tol: float = 1e-14):
+           max_iter: int = 30, tol: float = 1e-14):
     """Levenberg-Marquardt on the pixel reprojection error over all points, run to convergence
-    (the survey's probe shows cv2's answer is the converged minimiser to <= 2.4e-6 deg)."""
+    (the survey's probe shows cv2's answer is the converged minimiser to <= 2.4e-6 deg).  The cap of 30
+    iterations (OpenCV's own LM is capped at 20) is never reached on realistic corners: convergence takes < 15."""
     fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
 
     def residual(Rm, tv):

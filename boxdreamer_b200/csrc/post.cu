@@ -277,11 +277,13 @@ struct PnpProblem {
   double fx, fy, cx, cy;
   int n;
 };
+// The LM / cost routines take a point mask (bit i = use point i) so hypothesis refits can share one problem.
 
 BD_HD double reproj_cost(const PnpProblem& pb, const double (&R)[3][3], const double (&t)[3], double (*res)[2],
-                              double (*Xc)[3]) {
+                              double (*Xc)[3], unsigned mask = 0xffffffffu) {
   double cost = 0.0;
   for (int i = 0; i < pb.n; ++i) {
+    if (!((mask >> i) & 1u)) { if (res) { res[i][0] = 0.0; res[i][1] = 0.0; } continue; }
     double xc[3];
     for (int a = 0; a < 3; ++a) xc[a] = R[a][0] * pb.X[i][0] + R[a][1] * pb.X[i][1] + R[a][2] * pb.X[i][2] + t[a];
     const double ru = pb.fx * xc[0] / xc[2] + pb.cx - pb.uv[i][0];
@@ -346,14 +348,15 @@ BD_HD void pnp_dlt_init(const PnpProblem& pb, double (&R)[3][3], double (&t)[3])
   nearest_rotation(R, 60);
 }
 
-BD_HD void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int max_iter) {
+BD_HD void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int max_iter, unsigned mask = 0xffffffffu) {
   double res[PNP_MAXPTS][2], Xc[PNP_MAXPTS][3];
   double lam = 1e-3;
-  double cost = reproj_cost(pb, R, t, res, Xc);
+  double cost = reproj_cost(pb, R, t, res, Xc, mask);
   for (int it = 0; it < max_iter; ++it) {
     double H[6][6], g[6];
     for (int a = 0; a < 6; ++a) { g[a] = 0.0; for (int b = 0; b < 6; ++b) H[a][b] = 0.0; }
     for (int i = 0; i < pb.n; ++i) {
+      if (!((mask >> i) & 1u)) continue;
       const double x = Xc[i][0], y = Xc[i][1], z = Xc[i][2];
       const double du[3] = {pb.fx / z, 0.0, -pb.fx * x / (z * z)};
       const double dv[3] = {0.0, pb.fy / z, -pb.fy * y / (z * z)};
@@ -385,7 +388,7 @@ BD_HD void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int m
         tn[a] = t[a] + delta[3 + a];
       }
       double resn[PNP_MAXPTS][2], Xcn[PNP_MAXPTS][3];
-      const double cn = reproj_cost(pb, Rn, tn, resn, Xcn);
+      const double cn = reproj_cost(pb, Rn, tn, resn, Xcn, mask);
       if (isfinite(cn) && cn <= cost) {
         improved = true;
         step = 0.0;
@@ -440,12 +443,135 @@ __global__ void __launch_bounds__(64) pnp_iterative_kernel(const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// PnP, hypothesis mode (the robust counterpart of cv2.solvePnPRansac, box_utils.py:158-166 / 266-275): one warp per
+// query, one lane per hypothesis.  The all-point solution (DLT -> LM) seeds every hypothesis; hypothesis h refits the
+// pose on a subset of the points (all 6-, 5- and 4-subsets in turn, then seeded random 5-subsets) with a few LM
+// steps, is scored on ALL points (inlier count at thr_px, then truncated squared error), the warp arg-max wins and
+// is polished by LM on its inlier set.  Everything stays on the device; nothing is discarded.
+
+__device__ unsigned nth_subset_mask(int n, int k, int idx) {  // idx-th k-subset of n points in lexicographic order
+  unsigned mask = 0;
+  int x = 0;
+  for (int i = 0; i < k; ++i) {
+    for (;; ++x) {
+      // number of subsets that start with x at position i: C(n - x - 1, k - i - 1)
+      int c = 1, nn = n - x - 1, kk = k - i - 1;
+      for (int j = 0; j < kk; ++j) c = c * (nn - j) / (j + 1);
+      if (idx < c) break;
+      idx -= c;
+    }
+    mask |= 1u << x;
+    ++x;
+  }
+  return mask;
+}
+__device__ int n_choose_k(int n, int k) {
+  int c = 1;
+  for (int j = 0; j < k; ++j) c = c * (n - j) / (j + 1);
+  return c;
+}
+
+__global__ void __launch_bounds__(128) pnp_hypothesis_kernel(const float* __restrict__ corners, const float* __restrict__ bbox3d,
+                                                             const float* __restrict__ Kmat, float* __restrict__ poses, int B,
+                                                             int n_pts, int n_hyp, float thr_px, unsigned seed, int max_iter) {
+  __shared__ PnpProblem s_pb[4];
+  __shared__ double s_seed[4][12];
+  const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 4 + wq;
+  if (q >= B) return;
+  PnpProblem& pb = s_pb[wq];
+  if (lane == 0) {
+    pb.n = n_pts;
+    for (int i = 0; i < n_pts; ++i) {
+      for (int a = 0; a < 3; ++a) pb.X[i][a] = static_cast<double>(bbox3d[(static_cast<long long>(q) * n_pts + i) * 3 + a]);
+      for (int a = 0; a < 2; ++a) pb.uv[i][a] = static_cast<double>(corners[(static_cast<long long>(q) * n_pts + i) * 2 + a]);
+    }
+    const float* Kq = Kmat + static_cast<long long>(q) * 9;
+    pb.fx = Kq[0]; pb.fy = Kq[4]; pb.cx = Kq[2]; pb.cy = Kq[5];
+    double R[3][3], t[3];
+    pnp_dlt_init(pb, R, t);
+    pnp_lm(pb, R, t, max_iter);
+    for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) s_seed[wq][a * 3 + b] = R[a][b]; s_seed[wq][9 + a] = t[a]; }
+  }
+  __syncwarp();
+  const unsigned all_mask = (n_pts >= 32) ? 0xffffffffu : ((1u << n_pts) - 1u);
+  const double thr2 = static_cast<double>(thr_px) * thr_px;
+  const int c6 = n_pts >= 6 ? n_choose_k(n_pts, 6) : 0, c5 = n_pts >= 5 ? n_choose_k(n_pts, 5) : 0, c4 = n_choose_k(n_pts, 4);
+  // best-so-far of this lane; hypothesis "-1" is the all-point seed itself
+  double bestR[3][3], bestT[3];
+  int best_inl = -1;
+  double best_err = 1e300;
+  unsigned best_mask = all_mask;
+  for (int h = lane - 1; h < n_hyp; h += 32) {
+    double R[3][3], t[3];
+    for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) R[a][b] = s_seed[wq][a * 3 + b]; t[a] = s_seed[wq][9 + a]; }
+    if (h >= 0) {
+      unsigned m;
+      if (h < c6) m = nth_subset_mask(n_pts, 6, h);
+      else if (h < c6 + c5) m = nth_subset_mask(n_pts, 5, h - c6);
+      else if (h < c6 + c5 + c4) m = nth_subset_mask(n_pts, 4, h - c6 - c5);
+      else {
+        unsigned x = seed ^ (static_cast<unsigned>(q) * 2654435761u) ^ (static_cast<unsigned>(h) * 40503u);
+        x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+        m = nth_subset_mask(n_pts, 5, static_cast<int>(x % static_cast<unsigned>(c5 > 0 ? c5 : 1)));
+      }
+      pnp_lm(pb, R, t, 6, m);
+    }
+    double res[PNP_MAXPTS][2];
+    reproj_cost(pb, R, t, res, nullptr, all_mask);
+    int inl = 0;
+    double err = 0.0;
+    unsigned im = 0;
+    for (int i = 0; i < n_pts; ++i) {
+      const double e2 = res[i][0] * res[i][0] + res[i][1] * res[i][1];
+      if (e2 <= thr2) { ++inl; im |= 1u << i; }
+      err += fmin(e2, thr2);
+    }
+    bool ok = isfinite(err);
+    for (int a = 0; a < 3; ++a) ok = ok && isfinite(t[a]);
+    if (ok && (inl > best_inl || (inl == best_inl && err < best_err))) {
+      best_inl = inl; best_err = err; best_mask = im;
+      for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) bestR[a][b] = R[a][b]; bestT[a] = t[a]; }
+    }
+  }
+  // warp arg-max on (inliers, -err, -lane)
+  int win = lane;
+  int w_inl = best_inl;
+  double w_err = best_err;
+  for (int o = 16; o > 0; o >>= 1) {
+    const int o_inl = __shfl_xor_sync(0xffffffffu, w_inl, o);
+    const double o_err = __shfl_xor_sync(0xffffffffu, w_err, o);
+    const int o_win = __shfl_xor_sync(0xffffffffu, win, o);
+    if (o_inl > w_inl || (o_inl == w_inl && (o_err < w_err || (o_err == w_err && o_win < win)))) { w_inl = o_inl; w_err = o_err; win = o_win; }
+  }
+  if (lane == win) {
+    float* P = poses + static_cast<long long>(q) * 16;
+    for (int i = 0; i < 16; ++i) P[i] = 0.f;
+    if (best_inl >= 0) {
+      if (best_inl >= 4 && best_mask != all_mask) pnp_lm(pb, bestR, bestT, max_iter, best_mask);  // polish on the inliers
+      bool ok = true;
+      for (int a = 0; a < 3; ++a) { ok = ok && isfinite(bestT[a]); for (int b = 0; b < 3; ++b) ok = ok && isfinite(bestR[a][b]); }
+      if (ok) {
+        for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) P[a * 4 + b] = static_cast<float>(bestR[a][b]); P[a * 4 + 3] = static_cast<float>(bestT[a]); }
+        P[15] = 1.0f;
+      }
+    }
+  }
+}
+
 cudaError_t pnp_solve(const float* corners_px, const float* bbox3d, const float* K, float* poses, const PnpOpts& o, int B,
                       int n_pts, cudaStream_t s) {
   if (B <= 0) return cudaSuccess;
   if (n_pts < 6 || n_pts > PNP_MAXPTS) return cudaErrorInvalidValue;
-  if (o.mode != 0) return cudaErrorNotSupported;
+  if (o.mode != 0 && o.mode != 1) return cudaErrorNotSupported;
   const int max_iter = o.max_iter > 0 ? o.max_iter : 30;  // converged within 15 on realistic corners; OpenCV caps its LM at 20
+  if (o.mode == 1) {
+    const int n_hyp = o.n_hyp > 0 ? o.n_hyp : 154;
+    const float thr = o.thr_px > 0.f ? o.thr_px : 2.0f;
+    pnp_hypothesis_kernel<<<(B + 3) / 4, 128, 0, s>>>(corners_px, bbox3d, K, poses, B, n_pts, n_hyp, thr, o.seed, max_iter);
+    return cudaGetLastError();
+  }
   pnp_iterative_kernel<<<(B + 63) / 64, 64, 0, s>>>(corners_px, bbox3d, K, poses, B, n_pts, max_iter);
   return cudaGetLastError();
 }

@@ -295,10 +295,11 @@ BD_HD double reproj_cost(const PnpProblem& pb, const double (&R)[3][3], const do
   return cost;
 }
 
-BD_HD void pnp_dlt_init(const PnpProblem& pb, double (&R)[3][3], double (&t)[3]) {
+BD_HD void pnp_dlt_init(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], unsigned mask = 0xffffffffu) {
   double A[144], V[144];
   for (int i = 0; i < 144; ++i) A[i] = 0.0;
   for (int i = 0; i < pb.n; ++i) {
+    if (!((mask >> i) & 1u)) continue;
     const double xn = (pb.uv[i][0] - pb.cx) / pb.fx, yn = (pb.uv[i][1] - pb.cy) / pb.fy;
     double r1[12], r2[12];
     for (int j = 0; j < 12; ++j) { r1[j] = 0.0; r2[j] = 0.0; }
@@ -445,9 +446,8 @@ __global__ void __launch_bounds__(64) pnp_iterative_kernel(const float* __restri
 
 // ---------------------------------------------------------------------------------------------
 // PnP, hypothesis mode (the robust counterpart of cv2.solvePnPRansac, box_utils.py:158-166 / 266-275): one warp per
-// query, one lane per hypothesis.  The all-point solution (DLT -> LM) seeds every hypothesis; hypothesis h refits the
-// pose on a subset of the points (all 6-, 5- and 4-subsets in turn, then seeded random 5-subsets) with a few LM
-// steps, is scored on ALL points (inlier count at thr_px, then truncated squared error), the warp arg-max wins and
+// query, one lane per hypothesis.  Hypotheses: every 6-point subset solved from scratch (DLT -> LM), then every 5- and
+// 4-point subset (and, beyond those, seeded random 5-subsets) refitted from the all-point solution with a few LM steps; each is scored on ALL points (inlier count at thr_px, then truncated squared error), the warp arg-max wins and
 // is polished by LM on its inlier set.  Everything stays on the device; nothing is discarded.
 
 __device__ unsigned nth_subset_mask(int n, int k, int idx) {  // idx-th k-subset of n points in lexicographic order
@@ -516,6 +516,7 @@ __global__ void __launch_bounds__(128) pnp_hypothesis_kernel(const float* __rest
         x ^= x << 13; x ^= x >> 17; x ^= x << 5;
         m = nth_subset_mask(n_pts, 5, static_cast<int>(x % static_cast<unsigned>(c5 > 0 ? c5 : 1)));
       }
+      if (h < c6) pnp_dlt_init(pb, R, t, m);  // 6-point subsets are solved from scratch (independent of the seed's basin)
       pnp_lm(pb, R, t, 6, m);
     }
     double res[PNP_MAXPTS][2];

@@ -167,3 +167,30 @@ def test_errors_are_loud(weights):
     bad = _to_cuda(synth.synth_inputs(1, 2, 210, seed=1))
     with pytest.raises(AssertionError):
         m(bad)  # betr.py:269-271
+
+
+def test_336px_long_sequence_config(weights):
+    """BASELINE config 4 geometry at a test-sized batch: 336 px crops (P = 576, DINOv2 pos-embed resampled to 24x24,
+    581 DINOv2 tokens) and N = T*P = 1728 decoder tokens (13.5 key tiles: exercises the trimmed tail tile)."""
+    from oracle import boxdreamer_oracle as O
+    from boxdreamer_b200.config import make_config
+    dec, dino = weights
+    B, T, S = 1, 3, 336
+    data = synth.synth_inputs(B, T, S, seed=91)
+    with torch.no_grad():
+        ref = O.forward(data, dec, dino, with_pnp=False)
+    for precision, dtype, tol_max in (("exact", torch.float32, 1e-4), ("bf16", torch.bfloat16, 1e-1)):
+        m = BoxDreamer(make_config(S), precision=precision)
+        m.load_state_dict(dec, strict=True)
+        m.rgb_encoder.model.load_state_dict(dino, strict=True)
+        m = m.cuda().eval()
+        d = _to_cuda({k: (v.to(dtype) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in data.items()})
+        eng = m._engine_for(d["images"], B, T)
+        feats = eng.dino_forward(d["images"].view(B * T, 3, S, S).contiguous())
+        heat, logits = eng.decoder_forward(d["bbox_feat"].contiguous(), feats, d["query_idx"], want_logits=True)
+        e = _scaled(logits.view(B, 576, 1568), ref["logits"])
+        print(f"336px {precision}: logits scaled max err {e:.3e}")
+        assert e <= tol_max, f"{precision}: {e:.3e}"
+        if precision == "exact":
+            px, nm, idx = eng.corners_topk(heat, want_idx=True)
+            assert torch.equal(torch.sort(idx.cpu().long(), dim=2).values, torch.sort(ref["topk_idx"], dim=2).values)

@@ -6,7 +6,8 @@
 //   * two 128-row query tiles share every K/V tile; the MMA warp interleaves  S0, S1, PV0, S0', PV1, S1', ...  so one
 //     tile's softmax (warps 2-5 / 6-9) overlaps the other tile's MMAs -- the tensor pipe only waits for the slower of
 //     the MMA stream and the two softmax groups;
-//   * P stays in tensor memory (TS-form PV MMA), aliased onto the first 64 columns of its S tile;
+//   * P stays in tensor memory (TS-form PV MMA) in its own columns, so S(j+1) is issued as soon as a softmax group
+//     holds S(j) in registers: in steady state the groups never wait for the tensor pipe (exp/MUFU-paced);
 //   * the running maximum is only advanced (and O rescaled in TMEM) when it grows by more than 2^8 -- stale maxima are
 //     exact because the same maximum scales P and the row sum;
 //   * the last K/V tile is trimmed to the next multiple of 16 keys (runtime UMMA N / K), which removes most of the
@@ -22,20 +23,23 @@ bool get_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
 
 static constexpr int A2_THREADS = 384;  // 3 warpgroups: {TMA, MMA, -, -}, softmax tile 0, softmax tile 1
 static constexpr int A2_BQ = 128;
-static constexpr int A2_BKV = 128;
 
 template <int HD>
 struct Att2Cfg {
+  static constexpr int BKV = (HD > 64) ? 96 : 128;   // keys per tile: S (BKV) + P (BKV/2) + O (HD) fp32 columns per query tile <= 256
   static constexpr int NQS = (HD + 63) / 64;
   static constexpr int Q_TILE = NQS * A2_BQ * 128;
-  static constexpr int K_TILE = NQS * A2_BKV * 128;
+  static constexpr int K_SUB = BKV * 128;
+  static constexpr int K_TILE = NQS * K_SUB;
   static constexpr int V_SUB = HD * 128;
-  static constexpr int V_TILE = 2 * V_SUB;
-  static constexpr int NSTG = (HD > 64) ? 2 : 4;
-  static constexpr int QBUF = (HD > 64) ? 1 : 2;   // item-level Q buffering: the next item's Q is prefetched when smem allows
+  static constexpr int V_TILE = 2 * V_SUB;            // always two 64-key boxes (the second one is half used when BKV = 96)
+  static constexpr int NSTG = (HD > 64) ? 3 : 4;
+  static constexpr int QBUF = (HD > 64) ? 1 : 2;      // item-level Q buffering: the next item's Q is prefetched when smem allows
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = QBUF * 2 * Q_TILE + NSTG * (K_TILE + V_TILE) + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 512;
+  static constexpr int S_OFF = 0, P_OFF = BKV, O_OFF = BKV + BKV / 2;   // column offsets inside a tile's 256-column half
+  static_assert(O_OFF + HD <= 256, "tile does not fit its TMEM half");
 };
 
 struct Att2Args {
@@ -47,8 +51,31 @@ struct Att2Args {
 };
 #define A2_TRACE(role, slot) do { if (args.trace != nullptr && blockIdx.x == 0 && (slot) < 512) args.trace[(role) * 512 + (slot)] = clock64(); } while (0)
 
-__device__ __forceinline__ uint32_t s_col(int g) { return static_cast<uint32_t>(g * 128); }
-__device__ __forceinline__ uint32_t o_col(int g) { return static_cast<uint32_t>(256 + g * 128); }
+// S_g = Q_g K^T : HD/16 UMMAs (128 x ncols x 16), operands in shared memory
+template <int HD>
+__device__ __forceinline__ void a2_issue_s(uint32_t d_tmem, uint32_t q_saddr, uint32_t k_saddr, int ncols) {
+  using Cfg = Att2Cfg<HD>;
+  const uint32_t idesc_s = make_idesc_bf16(A2_BQ, ncols);
+#pragma unroll
+  for (int k = 0; k < HD / 16; ++k) {
+    const uint64_t adesc = make_smem_desc_sw128(q_saddr + (k / 4) * (A2_BQ * 128)) + 2 * (k % 4);
+    const uint64_t bdesc = make_smem_desc_sw128(k_saddr + (k / 4) * Cfg::K_SUB) + 2 * (k % 4);
+    umma_ss_bf16_w(d_tmem, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
+  }
+}
+// O_g (+)= P_g V : ncols/16 UMMAs (128 x HD x 16), P from tensor memory, V^T from shared memory
+template <int HD>
+__device__ __forceinline__ void a2_issue_pv(uint32_t d_tmem, uint32_t p_tmem, uint32_t v_saddr, int ncols, bool first) {
+  using Cfg = Att2Cfg<HD>;
+  constexpr uint32_t idesc_o = make_idesc_bf16(A2_BQ, HD);
+#pragma unroll
+  for (int k = 0; k < Cfg::BKV / 16; ++k) {
+    if (k * 16 < ncols) {
+      const uint64_t bdesc = make_smem_desc_sw128(v_saddr + (k / 4) * Cfg::V_SUB) + 2 * (k % 4);
+      umma_ts_bf16_w(d_tmem, p_tmem + k * 8, bdesc, idesc_o, (first && k == 0) ? 0u : 1u);
+    }
+  }
+}
 
 template <int HD>
 __global__ void __launch_bounds__(A2_THREADS, 1)
@@ -56,9 +83,10 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmV, const Att2Args args) {
   using Cfg = Att2Cfg<HD>;
   constexpr int NSTG = Cfg::NSTG;
+  constexpr int QBUF = Cfg::QBUF;
+  constexpr int BKV = Cfg::BKV;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int QBUF = Cfg::QBUF;
   uint8_t* sQ = smem;                                  // [QBUF][2][Q_TILE]
   uint8_t* sK = sQ + QBUF * 2 * Cfg::Q_TILE;           // [NSTG][K_TILE]
   uint8_t* sV = sK + NSTG * Cfg::K_TILE;               // [NSTG][V_TILE]
@@ -69,10 +97,11 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* k_empty = k_full + NSTG;
   uint64_t* v_full = k_empty + NSTG;
   uint64_t* v_empty = v_full + NSTG;
-  uint64_t* s_full = v_empty + NSTG;        // [2]
-  uint64_t* p_full = s_full + 2;            // [2]
-  uint64_t* o_full = p_full + 2;            // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_full = v_empty + NSTG;        // [2]  MMA -> softmax: S_g(j) complete
+  uint64_t* s_free = s_full + 2;            // [2]  softmax -> MMA: S_g(j) is in registers, S_g may be overwritten
+  uint64_t* p_full = s_free + 2;            // [2]  softmax -> MMA: P_g(j) stored (and O_g rescaled)
+  uint64_t* pv_done = p_full + 2;           // [2]  MMA -> softmax: O_g += P_g(j) V_j complete
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -81,8 +110,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int n_qt = (seq - q_off + A2_BQ - 1) / A2_BQ;    // query tiles per sequence
   const int n_pairs = (n_qt + 1) / 2;
   const int n_items = args.BH * n_pairs;
-  const int n_kv = (seq + A2_BKV - 1) / A2_BKV;
-  const int tail_keys = seq - (n_kv - 1) * A2_BKV;       // 1..128 valid keys in the last tile
+  const int n_kv = (seq + BKV - 1) / BKV;
+  const int tail_keys = seq - (n_kv - 1) * BKV;          // 1..BKV valid keys in the last tile
   const int tail_cols = (tail_keys + 15) & ~15;          // MMA N / K extent of the last tile
 
   if (warp == 0 && lane == 0) {
@@ -99,8 +128,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
+      mbar_init(&s_free[g], 4);
       mbar_init(&p_full[g], 4);
-      mbar_init(&o_full[g], 1);
+      mbar_init(&pv_done[g], 1);
     }
     fence_barrier_init();
   }
@@ -111,14 +141,16 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  // broadcast through a shuffle so the compiler keeps the TMEM base (and everything derived from it) in uniform
+  // registers: otherwise every tcgen05.mma is wrapped in an R2UR "waterfall" loop that costs ~100 cycles per issue
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
-  // register budget: the two softmax warpgroups keep a whole 128-column S row per thread
+  // register budget: the two softmax warpgroups keep a whole S row per thread
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp, elected lane issues) =====================
+    {
       int st = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -129,71 +161,53 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int qb = it % QBUF;
         uint8_t* sQi = sQ + qb * 2 * Cfg::Q_TILE;
         mbar_wait(&q_empty[qb], ((it / QBUF) & 1) ^ 1);  // the item that used this Q buffer has issued all its S MMAs
-        mbar_expect_tx(&q_full[qb * 2 + 0], Cfg::Q_TILE);
+        mbar_expect_tx_w(&q_full[qb * 2 + 0], Cfg::Q_TILE);
 #pragma unroll
-        for (int s = 0; s < Cfg::NQS; ++s) tma_load_2d(sQi + s * (A2_BQ * 128), &tmQ, &q_full[qb * 2 + 0], s * 64, bh * seq_pad + q0);
+        for (int s = 0; s < Cfg::NQS; ++s) tma_load_2d_w(sQi + s * (A2_BQ * 128), &tmQ, &q_full[qb * 2 + 0], s * 64, bh * seq_pad + q0);
         if (act1) {
-          mbar_expect_tx(&q_full[qb * 2 + 1], Cfg::Q_TILE);
+          mbar_expect_tx_w(&q_full[qb * 2 + 1], Cfg::Q_TILE);
 #pragma unroll
           for (int s = 0; s < Cfg::NQS; ++s)
-            tma_load_2d(sQi + Cfg::Q_TILE + s * (A2_BQ * 128), &tmQ, &q_full[qb * 2 + 1], s * 64, bh * seq_pad + q0 + A2_BQ);
+            tma_load_2d_w(sQi + Cfg::Q_TILE + s * (A2_BQ * 128), &tmQ, &q_full[qb * 2 + 1], s * 64, bh * seq_pad + q0 + A2_BQ);
         }
         for (int j = 0; j < n_kv; ++j) {
           mbar_wait(&k_empty[st], ph ^ 1);
-          mbar_expect_tx(&k_full[st], Cfg::K_TILE);
+          mbar_expect_tx_w(&k_full[st], Cfg::K_TILE);
 #pragma unroll
           for (int s = 0; s < Cfg::NQS; ++s)
-            tma_load_2d(sK + st * Cfg::K_TILE + s * (A2_BKV * 128), &tmK, &k_full[st], s * 64, bh * seq_pad + j * A2_BKV);
+            tma_load_2d_w(sK + st * Cfg::K_TILE + s * Cfg::K_SUB, &tmK, &k_full[st], s * 64, bh * seq_pad + j * BKV);
           mbar_wait(&v_empty[st], ph ^ 1);
-          mbar_expect_tx(&v_full[st], Cfg::V_TILE);
+          mbar_expect_tx_w(&v_full[st], Cfg::V_TILE);
 #pragma unroll
           for (int s = 0; s < 2; ++s)
-            tma_load_2d(sV + st * Cfg::V_TILE + s * Cfg::V_SUB, &tmV, &v_full[st], j * A2_BKV + s * 64, bh * HD);
+            tma_load_2d_w(sV + st * Cfg::V_TILE + s * Cfg::V_SUB, &tmV, &v_full[st], j * BKV + s * 64, bh * HD);
           if (++st == NSTG) { st = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_o = make_idesc_bf16(A2_BQ, HD);
+    // ===================== MMA issuer (whole warp, elected lane issues) =====================
+    {
       int st = 0;
       uint32_t ph = 0;
-      uint32_t p_cnt[2] = {0, 0};
+      uint32_t p_cnt[2] = {0, 0}, f_cnt[2] = {0, 0};
       uint32_t q1_cnt[2] = {0, 0};  // q_full[.][1] only completes for items whose second tile is active
-      const uint8_t* sQi = sQ;
+      const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
+      const uint32_t tS0 = tmem_base + Cfg::S_OFF, tS1 = tmem_base + 256 + Cfg::S_OFF;
+      const uint32_t tP0 = tmem_base + Cfg::P_OFF, tP1 = tmem_base + 256 + Cfg::P_OFF;
+      const uint32_t tO0 = tmem_base + Cfg::O_OFF, tO1 = tmem_base + 256 + Cfg::O_OFF;
       int it = 0;
 
-      auto issue_s = [&](int g, int stage, int ncols) {
-        const uint32_t idesc_s = make_idesc_bf16(A2_BQ, ncols);
-        const uint32_t d = tmem_base + s_col(g);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sQi + g * Cfg::Q_TILE + (k / 4) * (A2_BQ * 128))) + 2 * (k % 4);
-          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + stage * Cfg::K_TILE + (k / 4) * (A2_BKV * 128))) + 2 * (k % 4);
-          umma_ss_bf16(d, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
-        }
-      };
-      auto issue_pv = [&](int g, int stage, int ncols, bool first) {
-        const uint32_t d = tmem_base + o_col(g);
-        const uint32_t a = tmem_base + s_col(g);  // P aliases the first 64 columns of S
-        const int ksteps = ncols / 16;
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sV + stage * Cfg::V_TILE + (k / 4) * Cfg::V_SUB)) + 2 * (k % 4);
-          umma_ts_bf16(d, a + k * 8, bdesc, idesc_o, (first && k == 0) ? 0u : 1u);
-        }
-      };
-
-      // Issue order (tile 1 trails tile 0 by one step so the two softmax groups alternate on the MUFU pipe instead of
-      // running in lock-step):
-      //   S0(0) | j=0: PV0(0) S0(1) S1(0) | j: PV0(j) S0(j+1) PV1(j-1) S1(j) | ... | PV1(n-1)
+      // Issue order per item:  S0(0) S1(0) | for j: [S0(j+1) S1(j+1) as soon as the softmax groups hold S(j) in registers]
+      // PV0(j) PV1(j).  S(j+1) is therefore already complete when a group finishes tile j: the groups never wait for the
+      // tensor pipe in steady state and the kernel runs at the pace of the exp (MUFU) pipe.
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int pair = item % n_pairs;
         const int q0 = q_off + pair * 2 * A2_BQ;
         const bool act1 = q0 + A2_BQ < seq;
         const int qb = it % QBUF;
         uint64_t* q_empty_i = &q_empty[qb];
-        sQi = sQ + qb * 2 * Cfg::Q_TILE;
+        const uint32_t q_a = sQ_a + qb * 2 * Cfg::Q_TILE;
         mbar_wait(&q_full[qb * 2 + 0], (it / QBUF) & 1);
         if (act1) {
           mbar_wait(&q_full[qb * 2 + 1], q1_cnt[qb] & 1);
@@ -201,67 +215,60 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         mbar_wait(&k_full[st], ph);
         tc_fence_after();
-        issue_s(0, st, (n_kv == 1) ? tail_cols : A2_BKV);
-        umma_commit(&s_full[0]);
-        if (!act1) {  // tile 1 inactive: K_0 is only read by S0(0)
-          umma_commit(&k_empty[st]);
-          if (n_kv == 1) umma_commit(q_empty_i);
+        {
+          const int nc0 = (n_kv == 1) ? tail_cols : BKV;
+          a2_issue_s<HD>(tS0, q_a, sK_a + st * Cfg::K_TILE, nc0);
+          umma_commit_w(&s_full[0]);
+          if (act1) {
+            a2_issue_s<HD>(tS1, q_a + Cfg::Q_TILE, sK_a + st * Cfg::K_TILE, nc0);
+            umma_commit_w(&s_full[1]);
+          }
+          umma_commit_w(&k_empty[st]);
+          if (n_kv == 1) umma_commit_w(q_empty_i);
         }
-        int st_prev = st;  // stage of K/V tile j-1 (still needed by tile 1)
         for (int j = 0; j < n_kv; ++j) {
-          const int nc = (j == n_kv - 1) ? tail_cols : A2_BKV;
+          const int nc = (j == n_kv - 1) ? tail_cols : BKV;
           const bool has_next = j + 1 < n_kv;
           const int st_next = (st + 1 == NSTG) ? 0 : st + 1;
           const uint32_t ph_next = (st + 1 == NSTG) ? (ph ^ 1) : ph;
-          const int nc_next = (j + 1 == n_kv - 1) ? tail_cols : A2_BKV;
-          // ---- tile 0: O0 += P0(j) V_j, then S0(j+1) ----
+          if (has_next) {
+            const int nc_next = (j + 1 == n_kv - 1) ? tail_cols : BKV;
+            mbar_wait(&k_full[st_next], ph_next);
+            mbar_wait(&s_free[0], f_cnt[0] & 1);
+            ++f_cnt[0];
+            tc_fence_after();
+            a2_issue_s<HD>(tS0, q_a, sK_a + st_next * Cfg::K_TILE, nc_next);
+            umma_commit_w(&s_full[0]);
+            if (act1) {
+              mbar_wait(&s_free[1], f_cnt[1] & 1);
+              ++f_cnt[1];
+              tc_fence_after();
+              a2_issue_s<HD>(tS1, q_a + Cfg::Q_TILE, sK_a + st_next * Cfg::K_TILE, nc_next);
+              umma_commit_w(&s_full[1]);
+            }
+            umma_commit_w(&k_empty[st_next]);
+            if (j + 1 == n_kv - 1) umma_commit_w(q_empty_i);  // last S MMAs of this item issued
+          }
           mbar_wait(&v_full[st], ph);
-          A2_TRACE(0, (it * n_kv + j) * 4 + 0);
+          if (lane == 0) A2_TRACE(0, (it * n_kv + j) * 4 + 0);
           mbar_wait(&p_full[0], p_cnt[0] & 1);
-          A2_TRACE(0, (it * n_kv + j) * 4 + 1);
+          if (lane == 0) A2_TRACE(0, (it * n_kv + j) * 4 + 1);
           ++p_cnt[0];
           tc_fence_after();
-          issue_pv(0, st, nc, j == 0);
-          if (!has_next) umma_commit(&o_full[0]);
-          if (!act1) umma_commit(&v_empty[st]);
-          if (has_next) {
-            mbar_wait(&k_full[st_next], ph_next);
-            tc_fence_after();
-            issue_s(0, st_next, nc_next);
-            umma_commit(&s_full[0]);
-            if (!act1) {
-              umma_commit(&k_empty[st_next]);
-              if (j + 1 == n_kv - 1) umma_commit(q_empty_i);
-            }
-          }
-          // ---- tile 1, one step behind: O1 += P1(j-1) V_{j-1}, then S1(j) ----
+          a2_issue_pv<HD>(tO0, tP0, sV_a + st * Cfg::V_TILE, nc, j == 0);
+          umma_commit_w(&pv_done[0]);
           if (act1) {
-            if (j > 0) {
-              const int ncp = A2_BKV;  // tile j-1 is never the last one here
-              A2_TRACE(0, (it * n_kv + j) * 4 + 2);
-              mbar_wait(&p_full[1], p_cnt[1] & 1);
-              A2_TRACE(0, (it * n_kv + j) * 4 + 3);
-              ++p_cnt[1];
-              tc_fence_after();
-              issue_pv(1, st_prev, ncp, j == 1);
-              umma_commit(&v_empty[st_prev]);
-            }
-            issue_s(1, st, nc);
-            umma_commit(&s_full[1]);
-            umma_commit(&k_empty[st]);
-            if (!has_next) umma_commit(q_empty_i);  // last S MMAs of this item issued
+            if (lane == 0) A2_TRACE(0, (it * n_kv + j) * 4 + 2);
+            mbar_wait(&p_full[1], p_cnt[1] & 1);
+            if (lane == 0) A2_TRACE(0, (it * n_kv + j) * 4 + 3);
+            ++p_cnt[1];
+            tc_fence_after();
+            a2_issue_pv<HD>(tO1, tP1, sV_a + st * Cfg::V_TILE, nc, j == 0);
+            umma_commit_w(&pv_done[1]);
           }
-          st_prev = st;
+          umma_commit_w(&v_empty[st]);
           st = st_next;
           ph = ph_next;
-        }
-        if (act1) {  // drain: PV1(n-1)
-          mbar_wait(&p_full[1], p_cnt[1] & 1);
-          ++p_cnt[1];
-          tc_fence_after();
-          issue_pv(1, st_prev, tail_cols, n_kv == 1);
-          umma_commit(&o_full[1]);
-          umma_commit(&v_empty[st_prev]);
         }
       }
     }
@@ -273,10 +280,11 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int quad = warp & 3;              // TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_addr + s_col(g);
-    const uint32_t t_o = tmem_base + lane_addr + o_col(g);
+    const uint32_t t_s = tmem_base + lane_addr + g * 256 + Cfg::S_OFF;
+    const uint32_t t_p = tmem_base + lane_addr + g * 256 + Cfg::P_OFF;
+    const uint32_t t_o = tmem_base + lane_addr + g * 256 + Cfg::O_OFF;
     const float c = args.scale_log2;
-    uint32_t s_cnt = 0, o_cnt = 0;
+    uint32_t s_cnt = 0, d_cnt = 0;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int bh = item / n_pairs, pair = item % n_pairs;
@@ -284,32 +292,35 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (q0 >= seq) continue;  // inactive second tile: the whole group skips this item
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < n_kv; ++j) {
-        const int kv0 = j * A2_BKV;
+        const int kv0 = j * BKV;
         const bool last = (j == n_kv - 1);
         if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 4 + 0);
         mbar_wait(&s_full[g], s_cnt & 1);
         if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 4 + 1);
         ++s_cnt;
         tc_fence_after();
-        if (!last || tail_keys == A2_BKV) {
+        float alpha = 1.0f;
+        if (!last || tail_keys == BKV) {
           // ---------- full tile: the whole S row lives in registers (one TMEM read, no masking) ----------
-          uint32_t sv[128];
-          tmem_ld_32x32b_x32p(t_s + 0, sv + 0);
-          tmem_ld_32x32b_x32p(t_s + 32, sv + 32);
-          tmem_ld_32x32b_x32p(t_s + 64, sv + 64);
-          tmem_ld_32x32b_x32p(t_s + 96, sv + 96);
+          uint32_t sv[BKV];
+#pragma unroll
+          for (int ch = 0; ch < BKV / 32; ++ch) tmem_ld_32x32b_x32p(t_s + ch * 32, sv + ch * 32);
           tmem_wait_ld();
+          if (!last) {  // S_g may be overwritten by S_g(j+1) from now on
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[g]);
+          }
           if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 4 + 2);
           float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 128; i += 8) {
+          for (int i = 0; i < BKV; i += 8) {
             mx0 = fmax3(mx0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
             mx1 = fmax3(mx1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
             mx2 = fmax3(mx2, __uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5]));
             mx3 = fmax3(mx3, __uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7]));
           }
           const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-          float alpha = 1.0f;
           if (j == 0) {
             m_run = mx;
           } else if ((mx - m_run) * c > 8.0f) {  // lazy maximum: move only when it grew by more than 2^8
@@ -320,7 +331,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float nmc = -m_run * c;
           float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 64; i += 2) {
+          for (int i = 0; i < BKV / 2; i += 2) {
             const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), c, nmc));
             const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), c, nmc));
             const float p2 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 2]), c, nmc));
@@ -329,21 +340,15 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             sv[i] = pack_bf16x2(p0, p1);       // in place: word i is written after elements 2i, 2i+1 were consumed
             sv[i + 1] = pack_bf16x2(p2, p3);
           }
-          tmem_st_32x32b_x32p(t_s + 0, sv + 0);
-          tmem_st_32x32b_x32p(t_s + 32, sv + 32);
           l_run += (ps0 + ps1) + (ps2 + ps3);
-          // O rescale, deferred until the S registers are dead (PV_g(j) is only issued after this group's arrival)
-          if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll
-            for (int ch = 0; ch < HD / 32; ++ch) {
-              uint32_t v[32];
-              tmem_ld_32x32b_x32(t_o + ch * 32, v);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-              tmem_st_32x32b_x32(t_o + ch * 32, v);
-            }
+          if (j > 0) {  // PV_g(j-1) must have finished reading P_g and writing O_g
+            mbar_wait(&pv_done[g], d_cnt & 1);
+            ++d_cnt;
+            tc_fence_after();
           }
+          tmem_st_32x32b_x32p(t_p + 0, sv + 0);
+          if constexpr (BKV == 128) tmem_st_32x32b_x32p(t_p + 32, sv + 32);
+          else tmem_st_32x32b_x16(t_p + 32, sv + 32);
         } else {
           // ---------- trimmed last tile: chunked, masked, two passes over TMEM ----------
           const int nchunks = (tail_cols + 31) / 32;
@@ -359,24 +364,17 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               mx = fmaxf(mx, sc);
             }
           }
-          float alpha = 1.0f;
           if (j == 0) {
             m_run = mx;
           } else if ((mx - m_run) * c > 8.0f) {
             alpha = ex2_approx((m_run - mx) * c);
             m_run = mx;
           }
-          if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll
-            for (int ch = 0; ch < HD / 32; ++ch) {
-              uint32_t v[32];
-              tmem_ld_32x32b_x32(t_o + ch * 32, v);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-              tmem_st_32x32b_x32(t_o + ch * 32, v);
-            }
-            l_run *= alpha;
+          l_run *= alpha;
+          if (j > 0) {
+            mbar_wait(&pv_done[g], d_cnt & 1);
+            ++d_cnt;
+            tc_fence_after();
           }
           const float nmc = -m_run * c;
           float psum = 0.f;
@@ -394,9 +392,21 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               psum += p0 + p1;
               w[i] = pack_bf16x2(p0, p1);
             }
-            tmem_st_32x32b_x16(t_s + ch * 16, w);
+            tmem_st_32x32b_x16(t_p + ch * 16, w);
           }
           l_run += psum;
+        }
+        // O rescale (rare: lazy maximum), after PV_g(j-1) completed and with the S registers dead
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+          for (int ch = 0; ch < HD / 32; ++ch) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_o + ch * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x32(t_o + ch * 32, v);
+          }
         }
         tmem_wait_st();
         tc_fence_before();
@@ -405,8 +415,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 4 + 3);
       }
       // ---- epilogue: O / l -> bf16, token-major ----
-      mbar_wait(&o_full[g], o_cnt & 1);
-      ++o_cnt;
+      mbar_wait(&pv_done[g], d_cnt & 1);
+      ++d_cnt;
       tc_fence_after();
       const float inv_l = 1.0f / l_run;
       const int row = q0 + r;
@@ -454,7 +464,7 @@ static cudaError_t launch_att2(const bf16* Q, const bf16* K, const bf16* Vt, bf1
   const int BH = L * heads;
   CUtensorMap tq, tk, tv;
   if (!get_tmap_2d_bf16(&tq, Q, static_cast<uint64_t>(BH) * seq_pad, HD, HD, 64, A2_BQ)) return cudaErrorInvalidValue;
-  if (!get_tmap_2d_bf16(&tk, K, static_cast<uint64_t>(BH) * seq_pad, HD, HD, 64, A2_BKV)) return cudaErrorInvalidValue;
+  if (!get_tmap_2d_bf16(&tk, K, static_cast<uint64_t>(BH) * seq_pad, HD, HD, 64, Cfg::BKV)) return cudaErrorInvalidValue;
   if (!get_tmap_2d_bf16(&tv, Vt, static_cast<uint64_t>(BH) * HD, seq_pad, seq_pad, 64, HD)) return cudaErrorInvalidValue;
   auto kern = attn_tc2_kernel<HD>;
   static bool attr_set = false;

@@ -126,11 +126,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  // broadcast through a shuffle so the compiler keeps the TMEM base (and everything derived from it) in uniform
+  // registers: otherwise every tcgen05.mma is wrapped in an R2UR "waterfall" loop that costs ~100 cycles per issue
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp, elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -139,17 +141,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          mbar_expect_tx_w(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d_w(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d_w(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, elected lane issues) =====================
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      const uint32_t stage_a = smem_u32(stage_base);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -162,18 +165,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
+          const uint32_t sa = stage_a + stage * Cfg::STAGE_BYTES;
           const uint64_t adesc = make_smem_desc_sw128(sa);
           const uint64_t bdesc = make_smem_desc_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance along K inside the 128-byte swizzle row: +32 bytes -> +2 in the (addr >> 4) field
-            umma_ss_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_ss_bf16_w(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          umma_commit_w(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        umma_commit_w(&tfull_bar[acc]);  // accumulator complete -> epilogue
       }
     }
   } else if (warp >= EPI_WARP0) {

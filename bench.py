@@ -58,6 +58,31 @@ def flops_per_query(T=T_VIEWS, P=256, d=768, dec_layers=12, dino_layers=12, n_to
             "total": dino + betr_lin + betr_att + fusion + head}
 
 
+def ncu_traffic_bytes(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the newest committed
+    `ncu --set full` summary under profiles/ (scripts/ncu_summary.py output); None if no capture is committed."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_attention*.txt"))):
+        cur, rd, wr = None, None, None
+        for line in open(path):
+            if line.startswith("## "):
+                cur = line
+                rd = wr = None
+            elif cur and kernel_substr in cur:
+                m = re.match(r"\s+dram (read|write)\s+([0-9.]+) (\w+)", line)
+                if m:
+                    val = float(m.group(2)) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), 1)
+                    if m.group(1) == "read":
+                        rd = val
+                    else:
+                        wr = val
+                    if rd is not None and wr is not None:
+                        best = rd + wr
+    return best
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 
@@ -270,7 +295,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- in-step per-kernel timing (CUDA events on the launching stream, same workload) ----
     import ctypes as C
     _lib.check(lib.bd_profile_enable(eng.handle, 1))
-    ms_arr, n_arr = (C.c_double * 10)(), (C.c_int64 * 10)()
+    ncat = len(_lib.PROF_CATS)
+    ms_arr, n_arr = (C.c_double * ncat)(), (C.c_int64 * ncat)()
     _lib.check(lib.bd_profile_read(eng.handle, ms_arr, n_arr, 1))
     prof_steps = min(args.steps, 3)
     for _ in range(prof_steps):
@@ -280,20 +306,25 @@ def run_ours(args, rank, world, local_rank):
     kernel_ms = {name: (ms_arr[i] / prof_steps) for i, name in enumerate(_lib.PROF_CATS)}
     kernel_n = {name: int(n_arr[i] // prof_steps) for i, name in enumerate(_lib.PROF_CATS)}
 
-    # roofline of the attention kernel (north_star): QK^T and PV FLOPs only, 4*N^2*d per (sample, layer)
+    # roofline of the dominant north-star kernel: the decoder (BETR) attention kernel, attn_tc2_kernel<96>.
+    # Algorithmic FLOPs per launch = 4*N^2*d per sample (QK^T and PV only) x B samples; duration = in-step CUDA events.
     fl = flops_per_query()
-    att_flops_step = B * (fl["betr_attention"] + T * 12 * 4 * 261 * 261 * 768)
+    att_flops_launch = B * fl["betr_attention"] / 12.0
     att_launches = max(kernel_n["attention"], 1)
-    att_ms = kernel_ms["attention"]
+    att_ms_launch = kernel_ms["attention"] / att_launches
     peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-    achieved = att_flops_step / (att_ms / 1e3) / 1e12 if att_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "attn_tc_kernel (decoder 8x96 N=1536 + DINOv2 12x64 N=261)", "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
-                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
-                "flops_per_launch": att_flops_step / att_launches, "ms_per_launch": att_ms / att_launches,
-                "launches_per_step": att_launches}
+    achieved = att_flops_launch / (att_ms_launch / 1e3) / 1e12 if att_ms_launch > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "attn_tc2_kernel<96> (BETR joint attention, 8 heads x 96, N = T*P = 1536, B = 64)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "traffic": ncu_traffic_bytes("attn_tc2_kernel<96>"),
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}): kernel timed inside the step",
+                "flops_per_launch": att_flops_launch, "ms_per_launch": att_ms_launch, "launches_per_step": att_launches,
+                "algorithmic_bytes_per_launch": 4 * B * 8 * 1536 * 96 * 2}
+    dino_att_flops = B * T * 12 * 4 * 261 * 261 * 768
+    roofline_dino_attention = {"achieved": dino_att_flops / (kernel_ms["attention_dino"] / 1e3) / 1e12 if kernel_ms["attention_dino"] > 0 else 0.0,
+                               "peak": peak, "unit": "TFLOP/s", "ms_per_step": kernel_ms["attention_dino"]}
     gemm_ms = sum(kernel_ms[k] for k in ("gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_other"))
-    gemm_flops_step = B * (fl["total"] - fl["betr_attention"]) - B * T * 12 * 4 * 261 * 261 * 768
+    gemm_flops_step = B * (fl["total"] - fl["betr_attention"]) - dino_att_flops
     roofline_gemm = {"bound": "tensor", "achieved": gemm_flops_step / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0, "peak": peak,
                      "unit": "TFLOP/s"}
     roofline_gemm["frac"] = roofline_gemm["achieved"] / peak if peak else None
@@ -330,7 +361,8 @@ def run_ours(args, rank, world, local_rank):
                        "global_batch": world * B, "views": T, "img_size": S, "weights": "random-init (synth seed 0)",
                        "l2": "inputs (424 MB/step) exceed L2; no flush needed", "parallelism": f"query-shard x{world}",
                        "attn_variant": int(eng.cfg.attn_variant)},
-            "roofline": roofline, "roofline_gemm": roofline_gemm, "roofline_e2e": roofline_e2e,
+            "roofline": roofline, "roofline_gemm": roofline_gemm, "roofline_dino_attention": roofline_dino_attention,
+            "roofline_e2e": roofline_e2e,
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "bd_forward_host (C ABI, pinned host buffers)", "steps": e2e_steps},

@@ -364,7 +364,7 @@ static cudaError_t ln_act(bd_engine* e, const float* x, const float* w, const fl
 
 // one pre-LN transformer block on the fp32 residual stream X [L*seq, d]
 static int run_block(bd_engine* e, float* X, const std::string& p, int L, int seq, int seq_pad, int heads, int hd, float ln_eps,
-                     bool qk_norm, const char* g1, const char* g2, cudaStream_t s) {
+                     bool qk_norm, const char* g1, const char* g2, int attn_cat, cudaStream_t s) {
   const int M = L * seq, d = e->d;
   LAUNCH(BD_PROF_LAYERNORM, 1, ln_act(e, X, WF(e, p + "norm1.weight"), WF(e, p + "norm1.bias"), ln_eps, M, s));
   GemmEpi q;
@@ -374,7 +374,7 @@ static int run_block(bd_engine* e, float* X, const std::string& p, int L, int se
   q.k_norm_w = qk_norm ? WF(e, p + "attn.k_norm.weight") : nullptr;
   q.seq = seq; q.seq_pad = seq_pad; q.heads = heads; q.head_dim = hd; q.rms_eps = 1e-6f;
   LAUNCH(BD_PROF_GEMM_QKV, e->tc ? 1 : 2, linear(e, e->H, p + "attn.qkv.weight", M, 3 * d, d, EPI_QKV, q, s));
-  LAUNCH(BD_PROF_ATTENTION, 1, attention(e, L, heads, hd, seq, seq_pad, s));
+  LAUNCH(attn_cat, 1, attention(e, L, heads, hd, seq, seq_pad, s));
   GemmEpi pr;
   pr.bias = WF(e, p + "attn.proj.bias"); pr.out_f32 = X; pr.ldo = d; pr.gamma = g1 ? WF(e, p + g1) : nullptr;
   LAUNCH(BD_PROF_GEMM_PROJ, 1, linear(e, e->O, p + "attn.proj.weight", M, d, d, EPI_RESID, pr, s));
@@ -403,7 +403,7 @@ static int dino_forward_impl(bd_engine* e, const void* images, int dtype, float*
                                              WF(e, "dino.register_tokens"), L, e->n_tok, e->cfg.dino_registers, d, s));
   for (int i = 0; i < e->cfg.dino_layers; ++i) {
     int r = run_block(e, e->X_dino, "dino.blocks." + std::to_string(i) + ".", L, e->n_tok, e->seqpad_dino, e->cfg.dino_heads,
-                      e->hd_dino, 1e-6f, false, "ls1.gamma", "ls2.gamma", s);
+                      e->hd_dino, 1e-6f, false, "ls1.gamma", "ls2.gamma", BD_PROF_ATTENTION_DINO, s);
     if (r != BD_OK) return r;
   }
   // final LayerNorm, patch tokens only (vision_transformer.py:263-267)
@@ -440,7 +440,7 @@ static int decoder_forward_impl(bd_engine* e, const void* bbox_feat, int dtype, 
   const int seq = T * P, seq_pad = (seq + 127) / 128 * 128;
   for (int i = 0; i < e->cfg.dec_layers; ++i) {
     int r = run_block(e, e->X_dec, "decoder.attn." + std::to_string(i) + ".", B, seq, seq_pad, e->cfg.dec_heads, e->hd_dec, 1e-5f,
-                      true, nullptr, nullptr, s);
+                      true, nullptr, nullptr, BD_PROF_ATTENTION, s);
     if (r != BD_OK) return r;
   }
   LAUNCH(BD_PROF_GLUE, 1, gather_query(e->X_dec, query_idx, e->tc ? nullptr : reinterpret_cast<float*>(e->Xq),

@@ -9,7 +9,7 @@ if [ "$NO_NCU" != "1" ]; then
 echo "=== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1150 -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --quick > gpurun_out/ncu_launch.log 2>&1; echo "exit $?"
 echo "=== ncu full: attention"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_tc2_kernel -s 60 -c 3 -o gpurun_out/prof_attn -f python bench.py --steps 1 --warmup 3 --quick > gpurun_out/ncu_attn.log 2>&1; echo "exit $?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_tc2_kernel -s 60 -c 2 -o gpurun_out/prof_attn -f python bench.py --steps 1 --warmup 3 --quick > gpurun_out/ncu_attn.log 2>&1; echo "exit $?"
 echo "=== ncu full: gemm"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 300 -c 4 -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 3 --quick > gpurun_out/ncu_gemm.log 2>&1; echo "exit $?"
 fi

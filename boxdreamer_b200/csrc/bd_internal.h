@@ -38,6 +38,8 @@ struct GemmEpi {
 
 // --- tensor-core path (gemm_tc.cu / attn_tc.cu) ---
 cudaError_t gemm_tc(const bf16* A, const bf16* W, int M, int N, int K, int epi, const GemmEpi& e, cudaStream_t s);
+// same contract, CTA pairs (cta_group::2, 256 x BN tiles): gemm_tc2.cu.  gemm_tc() dispatches to it unless BD_GEMM_PAIR=0.
+cudaError_t gemm_tc_pair(const bf16* A, const bf16* W, int M, int N, int K, int epi, const GemmEpi& e, cudaStream_t s);
 // Q,K [BH, seq_pad, hd] bf16, Vt [BH, hd, seq_pad] bf16 -> O [L*seq, heads*hd] bf16 (token-major)
 // variant: 0 = P staged in shared memory (SS), 1 = P kept in tensor memory (TS), 2 = persistent ping-pong kernel (attn_tc2.cu)
 cudaError_t attention_tc(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int head_dim, int seq,

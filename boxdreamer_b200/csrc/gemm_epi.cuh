@@ -1,0 +1,233 @@
+// Shared pieces of the tcgen05 GEMM kernels (gemm_tc.cu: one CTA per tile; gemm_tc2.cu: CTA pairs, cta_group::2):
+// tile constants, the argument block and the fused epilogue that drains one 128 x BN accumulator tile from TMEM.
+#pragma once
+#include "bd_internal.h"
+#include "common.cuh"
+
+namespace bd {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+static constexpr int UMMA_K = 16;
+static constexpr int GEMM_THREADS = 384;
+static constexpr int EPI_WARP0 = 4;
+static constexpr int N_EPI_WARPS = 8;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NSTAGE = 4;
+  static constexpr int STAGING_BYTES = N_EPI_WARPS * 32 * 32 * 4;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+  static constexpr int TMEM_COLS = 512;  // 2 accumulator stages of BN (<= 256) fp32 columns
+};
+
+struct GemmArgs {
+  int M, N, K;
+  GemmEpi e;
+};
+
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  // x * Phi(x) with Phi(x) - 0.5 = 0.5 erf(x / sqrt 2) as a degree-17 odd minimax polynomial on |x| <= 4 (clamped beyond,
+  // where Phi - 0.5 = +-0.49997): max |gelu error| 2.2e-5 in fp32 Horner form -- two orders below bf16 resolution --
+  // and no MUFU op, so the fc1 epilogue stays off the 16/clk/SM special-function pipe.
+  const float xc = fminf(fmaxf(x, -4.0f), 4.0f);
+  const float x2 = xc * xc;
+  float p = 8.062929977e-11f;
+  p = fmaf(p, x2, -7.003156417e-09f);
+  p = fmaf(p, x2, 2.716075885e-07f);
+  p = fmaf(p, x2, -6.294891059e-06f);
+  p = fmaf(p, x2, 9.890726931e-05f);
+  p = fmaf(p, x2, -1.133918807e-03f);
+  p = fmaf(p, x2, 9.877469438e-03f);
+  p = fmaf(p, x2, -6.641058494e-02f);
+  p = fmaf(p, x2, 3.989227133e-01f);
+  return x * fmaf(p, xc, 0.5f);
+}
+
+// staging tile: 32 rows x 32 words (128 B per row).  Two access patterns share it:
+//  (a) word-granular XOR swizzle (stage_write / stage_read): row-owner writes, row-wise 4-byte reads  (EPI_QKV)
+//  (b) 16-byte-chunk XOR swizzle (stage_write16 / stage_read16): row-owner writes 8 x 16 B, then each lane reads a
+//      16-byte chunk of 8 different rows -> 4 rows x 128 B per warp instruction, conflict-free both ways.
+__device__ __forceinline__ void stage_write(uint32_t* tile, int lane, const uint32_t (&w)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) tile[lane * 32 + (j ^ lane)] = w[j];
+}
+__device__ __forceinline__ uint32_t stage_read(const uint32_t* tile, int rr, int lane) {
+  return tile[rr * 32 + (lane ^ rr)];
+}
+__device__ __forceinline__ void stage_write16(uint32_t* tile, int lane, const uint32_t (&w)[32]) {
+  uint4* row = reinterpret_cast<uint4*>(tile + lane * 32);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) row[j ^ (lane & 7)] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+}
+__device__ __forceinline__ uint4 stage_read16(const uint32_t* tile, int row, int c4) {
+  return reinterpret_cast<const uint4*>(tile + row * 32)[c4 ^ (row & 7)];
+}
+
+// Drains this warp's 32 rows x (column share) of one accumulator tile.
+//   t_acc : TMEM address of the tile (lane quadrant and accumulator stage already applied)
+//   row_w : global row of this warp's first TMEM lane;  n_blk : N-tile index;  grp : column group of this warp
+template <int BN, int EPI, int HD>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_t* tile_s, uint32_t t_acc, int row_w, int n_blk,
+                                                   int lane, int grp) {
+  const GemmEpi& e = args.e;
+  const int M = args.M, N = args.N;
+  const int my_row = row_w + lane;
+  if constexpr (EPI != EPI_QKV) {
+    // 32-column chunks.  Row-owner phase: TMEM -> registers -> swizzled smem.  Row-wise phase: lane = (row group
+    // rsub, 16-byte column chunk c4); 8 independent 16-byte global accesses per lane are in flight at once.
+    long long my_out_row = my_row;
+    int my_tab_row = 0;
+    if (EPI == EPI_F32 && e.rp_in > 0) {
+      my_tab_row = my_row % e.rp_in;
+      my_out_row = static_cast<long long>(my_row / e.rp_in) * e.rp_out + e.rp_off + my_tab_row;
+    }
+    const int c4 = lane & 7, rsub = lane >> 3;
+    constexpr int NCH = BN / 64;  // chunks of 32 columns per column-half
+    for (int c = 0; c < NCH; ++c) {
+      const int col0 = n_blk * BN + grp * (BN / 2) + c * 32;
+      if (col0 >= N) continue;  // N tail: nothing to store (warp-uniform)
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(t_acc + grp * (BN / 2) + c * 32, v);
+      tmem_wait_ld();
+      stage_write16(tile_s, lane, v);
+      __syncwarp();
+      const int col = col0 + 4 * c4;
+      const bool col_ok = col < N;  // N % 4 == 0: a 16-byte chunk is entirely in or out
+      const float4 b4 = col_ok ? __ldg(reinterpret_cast<const float4*>(e.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 a[8];
+      long long orow[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + rsub;
+        const uint4 u = stage_read16(tile_s, row, c4);
+        a[i] = make_float4(__uint_as_float(u.x) + b4.x, __uint_as_float(u.y) + b4.y, __uint_as_float(u.z) + b4.z,
+                           __uint_as_float(u.w) + b4.w);
+        orow[i] = __shfl_sync(0xffffffffu, my_out_row, row);
+      }
+      if constexpr (EPI == EPI_F32) {
+        int trow[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) trow[i] = __shfl_sync(0xffffffffu, my_tab_row, 4 * i + rsub);
+        if (e.addtab != nullptr && col_ok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (row_w + 4 * i + rsub < M) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(e.addtab + static_cast<long long>(trow[i]) * N + col));
+              a[i].x += t4.x; a[i].y += t4.y; a[i].z += t4.z; a[i].w += t4.w;
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (row_w + 4 * i + rsub < M && col_ok) *reinterpret_cast<float4*>(e.out_f32 + orow[i] * e.ldo + col) = a[i];
+        }
+      } else if constexpr (EPI == EPI_RESID) {
+        const float4 g4 = (e.gamma != nullptr && col_ok) ? __ldg(reinterpret_cast<const float4*>(e.gamma + col))
+                                                          : make_float4(1.f, 1.f, 1.f, 1.f);
+        float4 r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {  // all residual loads first (memory-level parallelism), then the stores
+          r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_w + 4 * i + rsub < M && col_ok) r[i] = *reinterpret_cast<const float4*>(e.out_f32 + orow[i] * e.ldo + col);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (row_w + 4 * i + rsub < M && col_ok) {
+            r[i].x = fmaf(g4.x, a[i].x, r[i].x); r[i].y = fmaf(g4.y, a[i].y, r[i].y);
+            r[i].z = fmaf(g4.z, a[i].z, r[i].z); r[i].w = fmaf(g4.w, a[i].w, r[i].w);
+            *reinterpret_cast<float4*>(e.out_f32 + orow[i] * e.ldo + col) = r[i];
+          }
+        }
+      } else {  // EPI_GELU / EPI_ACT: bf16 store, 8 bytes per lane
+        bf16* out = reinterpret_cast<bf16*>(e.out_act);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if constexpr (EPI == EPI_GELU) {
+            a[i].x = gelu_erf_fast(a[i].x); a[i].y = gelu_erf_fast(a[i].y);
+            a[i].z = gelu_erf_fast(a[i].z); a[i].w = gelu_erf_fast(a[i].w);
+          }
+          if (row_w + 4 * i + rsub < M && col_ok) {
+            uint2 pk;
+            pk.x = pack_bf16x2(a[i].x, a[i].y);
+            pk.y = pack_bf16x2(a[i].z, a[i].w);
+            *reinterpret_cast<uint2*>(out + orow[i] * N + col) = pk;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else {  // EPI_QKV
+    static_assert(EPI != EPI_QKV || (BN % HD == 0), "BN must hold whole heads");
+    constexpr int UNITS = BN / HD;
+    constexpr int WPR = HD / 2;  // packed words per row
+    const int d_model = e.heads * HD;
+    const int l = my_row / e.seq, tok = my_row % e.seq;
+    const bool row_ok = my_row < M;
+    // element offset of (l, head 0, tok, 0) in Q/K; the head term is added per unit
+    const long long my_qk_off = (static_cast<long long>(l) * e.heads * e.seq_pad + tok) * HD;
+    for (int u = grp; u < UNITS; u += 2) {
+      const int col0 = n_blk * BN + u * HD;
+      if (col0 >= N) continue;
+      const int which = col0 / d_model;            // 0 q, 1 k, 2 v
+      const int head = (col0 % d_model) / HD;
+      float f[HD];
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_acc + u * HD + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[c * 32 + j] = __uint_as_float(v[j]) + __ldg(e.bias + col0 + c * 32 + j);
+      }
+      if (which < 2) {
+        const float* nw = (which == 0) ? e.q_norm_w : e.k_norm_w;
+        if (nw != nullptr) {
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < HD; ++j) ss = fmaf(f[j], f[j], ss);
+          const float r = rsqrtf(ss * (1.0f / HD) + e.rms_eps);
+#pragma unroll
+          for (int j = 0; j < HD; ++j) f[j] = f[j] * r * __ldg(nw + j);
+        }
+        bf16* base = reinterpret_cast<bf16*>(which == 0 ? e.q : e.k);
+        const long long head_off = static_cast<long long>(head) * e.seq_pad * HD;
+#pragma unroll
+        for (int piece = 0; piece < (WPR + 31) / 32; ++piece) {
+          uint32_t w[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int wi = piece * 32 + j;
+            w[j] = (wi < WPR) ? pack_bf16x2(f[2 * (wi < WPR ? wi : 0)], f[2 * (wi < WPR ? wi : 0) + 1]) : 0u;
+          }
+          stage_write(tile_s, lane, w);
+          __syncwarp();
+          const int wi = piece * 32 + lane;
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            const uint32_t word = stage_read(tile_s, rr, lane);
+            const long long off = __shfl_sync(0xffffffffu, my_qk_off, rr);
+            if (row_w + rr < M && wi < WPR) {
+              *reinterpret_cast<uint32_t*>(base + head_off + off + 2 * wi) = word;
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        // V^T [BH, HD, seq_pad]: lanes hold consecutive tokens -> coalesced along the key axis
+        bf16* vt = reinterpret_cast<bf16*>(e.v);
+        if (row_ok) {
+          bf16* dst = vt + (static_cast<long long>(l) * e.heads + head) * HD * e.seq_pad + tok;
+#pragma unroll
+          for (int j = 0; j < HD; ++j) dst[static_cast<long long>(j) * e.seq_pad] = __float2bfloat16_rn(f[j]);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace bd

@@ -1,0 +1,209 @@
+// CTA-pair tcgen05 GEMM (cta_group::2): a 256 x BN output tile per pair of SMs.
+//
+// A single-CTA tcgen05.mma with both operands in shared memory is operand-bandwidth bound (12 KB of smem reads per
+// 128-cycle 128x256x16 MMA).  In a CTA pair each SM stages its own 128 rows of A and only HALF of the B tile
+// (BN/2 rows); the pair's tensor cores share the B halves, so every SM reads 8 KB per MMA and writes 32 KB instead of
+// 48 KB per k-block through TMA -- the configuration cuBLAS uses to reach the B200 GEMM peak.
+//
+// Roles per CTA (12 warps, same as gemm_tc.cu): warp 0 TMA producer (both CTAs load their own tiles; the bytes are
+// accounted on the leader's mbarrier), warp 1 MMA issuer (leader CTA only; completion is multicast to both CTAs'
+// barriers), warp 2 TMEM allocator (collective cta_group::2 allocation), warps 4-11 the shared fused epilogue
+// (gemm_epi.cuh) on the CTA's own 128 accumulator rows.
+#include <string>
+
+#include "gemm_epi.cuh"
+
+namespace bd {
+
+bool get_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t bc, uint32_t br);
+
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NSTAGE = 6;
+  static constexpr int STAGING_BYTES = N_EPI_WARPS * 32 * 32 * 4;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 512;
+};
+
+template <int BN, int EPI, int HD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int NSTAGE = Cfg::NSTAGE;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint32_t* staging = reinterpret_cast<uint32_t*>(smem + NSTAGE * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
+  uint64_t* full_bar = bars;                       // [NSTAGE]  used in the leader: TMA bytes of BOTH CTAs
+  uint64_t* empty_bar = bars + NSTAGE;             // [NSTAGE]  each CTA: multicast commit of the leader's MMAs
+  uint64_t* tfull_bar = bars + 2 * NSTAGE;         // [2]       each CTA: accumulator complete (multicast commit)
+  uint64_t* tempty_bar = bars + 2 * NSTAGE + 2;    // [2]       leader: epilogue warps of both CTAs
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int M = args.M, N = args.N, K = args.K;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int tiles_m = (M + 2 * BM - 1) / (2 * BM);
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * N_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barriers of BOTH CTAs are initialised before anyone signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += npairs) {
+      const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+        if (leader) mbar_expect_tx_w(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+        tma_load_2d_2sm_w(sa, &tmA, leader_full, kb * BK, m_blk * 2 * BM + static_cast<int>(rank) * BM);
+        tma_load_2d_2sm_w(sb, &tmB, leader_full, kb * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+      const uint32_t stage_a = smem_u32(stage_base);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = stage_a + stage * Cfg::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sa);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_ss_bf16_2sm_w(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm_w(&empty_bar[stage], 0x3);   // frees the smem slot in both CTAs
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm_w(&tfull_bar[acc], 0x3);       // accumulator complete -> both epilogues
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int ew = warp - EPI_WARP0;
+    const int quad = warp & 3;
+    const int grp = ew >> 2;
+    uint32_t* tile_s = staging + ew * 1024;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+      const int row_w = m_blk * 2 * BM + static_cast<int>(rank) * BM + quad * 32;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      gemm_epilogue_tile<BN, EPI, HD>(args, tile_s, t_acc, row_w, n_blk, lane, grp);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tempty_bar[acc]);
+        else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer may still signal into this CTA
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+static int g_num_sms2 = 0;
+extern thread_local std::string g_tc_err_2;
+thread_local std::string g_tc_err_2;
+
+template <int BN, int EPI, int HD>
+static cudaError_t launch2(const bf16* A, const bf16* W, int M, int N, int K, const GemmEpi& e, cudaStream_t s) {
+  using Cfg = Gemm2Cfg<BN>;
+  CUtensorMap tmA, tmB;
+  if (!get_tmap_2d_bf16(&tmA, A, M, K, K, BK, BM)) return cudaErrorInvalidValue;
+  if (!get_tmap_2d_bf16(&tmB, W, N, K, K, BK, BN / 2)) return cudaErrorInvalidValue;
+  auto kern = gemm_tc2_kernel<BN, EPI, HD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (err != cudaSuccess) return err;
+    attr_set = true;
+  }
+  if (g_num_sms2 == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms2, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+  const int max_pairs = g_num_sms2 / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  GemmArgs args{M, N, K, e};
+  kern<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, args);
+  return cudaGetLastError();
+}
+
+cudaError_t gemm_tc_pair(const bf16* A, const bf16* W, int M, int N, int K, int epi, const GemmEpi& e, cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0 || (N % 4) != 0) return cudaErrorInvalidValue;
+  switch (epi) {
+    case EPI_F32: return launch2<256, EPI_F32, 32>(A, W, M, N, K, e, s);
+    case EPI_RESID: return launch2<256, EPI_RESID, 32>(A, W, M, N, K, e, s);
+    case EPI_GELU: return launch2<256, EPI_GELU, 32>(A, W, M, N, K, e, s);
+    case EPI_ACT: return launch2<256, EPI_ACT, 32>(A, W, M, N, K, e, s);
+    case EPI_QKV:
+      if (N != 3 * e.heads * e.head_dim || (e.heads * e.head_dim) % 192 != 0) return cudaErrorInvalidValue;
+      if (e.head_dim == 96) return launch2<192, EPI_QKV, 96>(A, W, M, N, K, e, s);
+      if (e.head_dim == 64) return launch2<192, EPI_QKV, 64>(A, W, M, N, K, e, s);
+      return cudaErrorInvalidValue;
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace bd

@@ -20,6 +20,19 @@ def _operands(M, N, K, seed):
     return A.cuda(), W.cuda(), b.cuda(), ref
 
 
+@pytest.fixture(params=[0, 1], ids=["cta1", "pair"])
+def gemm_pair(request):
+    """Runs the test once with the single-CTA GEMM and once with the CTA-pair (cta_group::2) GEMM."""
+    import os
+    old = os.environ.get("BD_GEMM_PAIR")
+    os.environ["BD_GEMM_PAIR"] = str(request.param)
+    yield request.param
+    if old is None:
+        os.environ.pop("BD_GEMM_PAIR", None)
+    else:
+        os.environ["BD_GEMM_PAIR"] = old
+
+
 @pytest.mark.parametrize("M,N,K", [
     (128, 256, 64),      # one tile, one k-block
     (128, 256, 256),     # one tile, 4 k-blocks (ring wrap-free)
@@ -29,7 +42,7 @@ def _operands(M, N, K, seed):
     (384, 768, 1568),    # K tail (bbox_emb)
     (20000, 768, 3072),  # more tiles than SMs (persistent loop), fc2 shape
 ])
-def test_gemm_tc_f32(lib, M, N, K):
+def test_gemm_tc_f32(lib, gemm_pair, M, N, K):
     A, W, b, ref = _operands(M, N, K, M + N + K)
     out = gemm(A, W, b, M, N, K, _lib.EPI_F32, TC)
     ok, msg = report(f"gemm_tc_f32[{M},{N},{K}]", out, ref, tol_rel=1e-5)
@@ -37,7 +50,7 @@ def test_gemm_tc_f32(lib, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 768, 768), (1000, 3072, 768)])
-def test_gemm_tc_epilogues(lib, M, N, K):
+def test_gemm_tc_epilogues(lib, gemm_pair, M, N, K):
     A, W, b, ref = _operands(M, N, K, 3 * M + N)
     out = gemm(A, W, b, M, N, K, _lib.EPI_ACT, TC)
     ok, msg = report("gemm_tc_act(bf16)", out, ref, tol_rel=6e-3)
@@ -74,7 +87,7 @@ def _qkv_case(L, seq, heads, hd, norm, seed):
 
 
 @pytest.mark.parametrize("L,seq,heads,hd,norm", [(2, 512, 8, 96, True), (3, 261, 12, 64, False), (1, 1536, 8, 96, True)])
-def test_qkv_project_tc(lib, L, seq, heads, hd, norm):
+def test_qkv_project_tc(lib, gemm_pair, L, seq, heads, hd, norm):
     x, W, b, qw, kw, q, k, v, seq_pad = _qkv_case(L, seq, heads, hd, norm, 17)
     Q = torch.zeros(L * heads, seq_pad, hd, device="cuda", dtype=torch.bfloat16)
     K = torch.zeros_like(Q)

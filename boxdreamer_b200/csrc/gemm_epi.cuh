@@ -48,6 +48,28 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return x * fmaf(p, xc, 0.5f);
 }
 
+// Two elements at once on the packed-fp32 pipe (FFMA2): x * Phi(x), Phi(x) - 0.5 = x * q(min(x^2, 16)) with q a degree-7
+// minimax polynomial in x^2 (max |gelu error| 3.8e-5 on |x| <= 4); beyond |x| = 4 the saturating fma clamps Phi to
+// [0, 1] (error there <= 4 * (1 - Phi(4)) = 1.3e-4 at x = 4, i.e. 3e-5 relative).
+__device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
+  const f32x2 X = pack_f32x2(x0, x1);
+  float s0, s1;
+  unpack_f32x2(mul_f32x2(X, X), s0, s1);
+  const f32x2 X2 = pack_f32x2(fminf(s0, 16.0f), fminf(s1, 16.0f));
+  f32x2 p = pack_f32x2(-1.301277620e-09f, -1.301277620e-09f);
+  p = fma_f32x2(p, X2, pack_f32x2(1.041950039e-07f, 1.041950039e-07f));
+  p = fma_f32x2(p, X2, pack_f32x2(-3.657106863e-06f, -3.657106863e-06f));
+  p = fma_f32x2(p, X2, pack_f32x2(7.485470993e-05f, 7.485470993e-05f));
+  p = fma_f32x2(p, X2, pack_f32x2(-1.006488016e-03f, -1.006488016e-03f));
+  p = fma_f32x2(p, X2, pack_f32x2(9.505389249e-03f, 9.505389249e-03f));
+  p = fma_f32x2(p, X2, pack_f32x2(-6.588782661e-02f, -6.588782661e-02f));
+  p = fma_f32x2(p, X2, pack_f32x2(3.986733839e-01f, 3.986733839e-01f));
+  float p0, p1;
+  unpack_f32x2(p, p0, p1);
+  x0 = x0 * __saturatef(fmaf(p0, x0, 0.5f));
+  x1 = x1 * __saturatef(fmaf(p1, x1, 0.5f));
+}
+
 // staging tile: 32 rows x 32 words (128 B per row).  Two access patterns share it:
 //  (a) word-granular XOR swizzle (stage_write / stage_read): row-owner writes, row-wise 4-byte reads  (EPI_QKV)
 //  (b) 16-byte-chunk XOR swizzle (stage_write16 / stage_read16): row-owner writes 8 x 16 B, then each lane reads a
@@ -227,6 +249,78 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_
         }
       }
     }
+  }
+}
+
+// TMA-out epilogue (EPI_GELU / EPI_ACT: bf16 store, EPI_RESID: fp32 reduce-add performed by the L2) for N % 64 == 0.
+// Each lane owns one accumulator row: TMEM -> registers -> bias / GELU / gamma -> 128-byte swizzled staging row ->
+// one elected TMA store of the 32-row box.  No per-element global address arithmetic, no residual load in the SM,
+// M tail clipped by the tensor map.  sbuf: this warp's two 4 KB staging boxes (1024-byte aligned), buf: toggles.
+template <int BN, int EPI>
+__device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmArgs& args, const CUtensorMap* tm_out, uint8_t* sbuf, uint32_t& buf,
+                                                       uint32_t t_acc, int row_w, int n_blk, int lane, int grp) {
+  static_assert(EPI == EPI_GELU || EPI == EPI_ACT || EPI == EPI_RESID, "TMA-out epilogue kinds");
+  const GemmEpi& e = args.e;
+  if (row_w >= args.M) return;  // whole 32-row slab beyond M (warp-uniform)
+  constexpr int CW = (EPI == EPI_RESID) ? 32 : 64;  // columns per 128-byte staging row
+  constexpr int NCH = (BN / 2) / CW;
+  const int sw = lane & 7;
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    const int colt = grp * (BN / 2) + c * CW;
+    const int col0 = n_blk * BN + colt;
+    if (col0 >= args.N) continue;
+    uint8_t* sb = sbuf + buf * 4096;
+    if (lane == 0) bulk_wait_group_read<1>();  // the store issued two chunks ago has finished reading this box
+    __syncwarp();
+    uint4* row = reinterpret_cast<uint4*>(sb + lane * 128);
+    if constexpr (EPI == EPI_RESID) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(t_acc + colt, v);
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+      const float4* g4 = reinterpret_cast<const float4*>(e.gamma + col0);
+      const bool has_g = e.gamma != nullptr;
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(b4 + j);  // warp-uniform address: one broadcast transaction
+        float4 o = make_float4(__uint_as_float(v[4 * j]) + b.x, __uint_as_float(v[4 * j + 1]) + b.y,
+                               __uint_as_float(v[4 * j + 2]) + b.z, __uint_as_float(v[4 * j + 3]) + b.w);
+        if (has_g) {
+          const float4 g = __ldg(g4 + j);
+          o.x *= g.x; o.y *= g.y; o.z *= g.z; o.w *= g.w;
+        }
+        row[j ^ sw] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w));
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_acc + colt + h * 32, v);
+        const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0 + h * 32);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // 8 columns -> one 16-byte chunk of bf16
+          const float4 ba = __ldg(b4 + 2 * j), bb = __ldg(b4 + 2 * j + 1);
+          float f0 = __uint_as_float(v[8 * j]) + ba.x, f1 = __uint_as_float(v[8 * j + 1]) + ba.y;
+          float f2 = __uint_as_float(v[8 * j + 2]) + ba.z, f3 = __uint_as_float(v[8 * j + 3]) + ba.w;
+          float f4 = __uint_as_float(v[8 * j + 4]) + bb.x, f5 = __uint_as_float(v[8 * j + 5]) + bb.y;
+          float f6 = __uint_as_float(v[8 * j + 6]) + bb.z, f7 = __uint_as_float(v[8 * j + 7]) + bb.w;
+          if constexpr (EPI == EPI_GELU) {
+            gelu_erf_fast2(f0, f1); gelu_erf_fast2(f2, f3); gelu_erf_fast2(f4, f5); gelu_erf_fast2(f6, f7);
+          }
+          row[(h * 4 + j) ^ sw] = make_uint4(pack_bf16x2(f0, f1), pack_bf16x2(f2, f3), pack_bf16x2(f4, f5), pack_bf16x2(f6, f7));
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (EPI == EPI_RESID) tma_reduce_add_2d(tm_out, sb, col0, row_w);
+      else tma_store_2d(tm_out, sb, col0, row_w);
+      bulk_commit_group();
+    }
+    buf ^= 1;
   }
 }
 

@@ -177,15 +177,16 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2D bf16 tensor [rows, cols] (cols contiguous, row pitch `pitch_elems`), box {box_cols, box_rows}, 128B swizzle, zero OOB fill.
-bool make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_cols,
-                       uint32_t box_rows) {
+// esz = 2: bf16 elements, esz = 4: fp32 elements (epilogue TMA stores / reduce-adds).
+static bool make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_cols,
+                         uint32_t box_rows, uint32_t esz) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { g_tc_err = "cuTensorMapEncodeTiled entry point unavailable"; return false; }
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {pitch_elems * 2};
+  cuuint64_t gstride[1] = {pitch_elems * esz};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = enc(out, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -196,29 +197,32 @@ bool make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_
 }
 
 struct TmapKey {
-  const void* p; uint64_t rows, cols, pitch; uint32_t bc, br;
+  const void* p; uint64_t rows, cols, pitch; uint32_t bc, br, esz;
   bool operator==(const TmapKey& o) const {
-    return p == o.p && rows == o.rows && cols == o.cols && pitch == o.pitch && bc == o.bc && br == o.br;
+    return p == o.p && rows == o.rows && cols == o.cols && pitch == o.pitch && bc == o.bc && br == o.br && esz == o.esz;
   }
 };
 struct TmapHash {
   size_t operator()(const TmapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.p);
-    h = h * 1000003u ^ k.rows; h = h * 1000003u ^ k.cols; h = h * 1000003u ^ k.pitch; h = h * 1000003u ^ k.bc; h = h * 1000003u ^ k.br;
+    h = h * 1000003u ^ k.rows; h = h * 1000003u ^ k.cols; h = h * 1000003u ^ k.pitch; h = h * 1000003u ^ k.bc; h = h * 1000003u ^ k.br; h = h * 1000003u ^ k.esz;
     return h;
   }
 };
 static std::unordered_map<TmapKey, CUtensorMap, TmapHash> g_tmaps;
 static std::mutex g_tmap_mu;
 
-bool get_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t bc, uint32_t br) {
+bool get_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t bc, uint32_t br, uint32_t esz) {
   std::lock_guard<std::mutex> lk(g_tmap_mu);
-  TmapKey k{ptr, rows, cols, pitch, bc, br};
+  TmapKey k{ptr, rows, cols, pitch, bc, br, esz};
   auto it = g_tmaps.find(k);
   if (it != g_tmaps.end()) { *out = it->second; return true; }
-  if (!make_tmap_2d_bf16(out, ptr, rows, cols, pitch, bc, br)) return false;
+  if (!make_tmap_2d(out, ptr, rows, cols, pitch, bc, br, esz)) return false;
   g_tmaps.emplace(k, *out);
   return true;
+}
+bool get_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t bc, uint32_t br) {
+  return get_tmap_2d(out, ptr, rows, cols, pitch, bc, br, 2);
 }
 
 template <int BN, int EPI, int HD>

@@ -9,6 +9,8 @@
 // accounted on the leader's mbarrier), warp 1 MMA issuer (leader CTA only; completion is multicast to both CTAs'
 // barriers), warp 2 TMEM allocator (collective cta_group::2 allocation), warps 4-11 the shared fused epilogue
 // (gemm_epi.cuh) on the CTA's own 128 accumulator rows.
+#include <stdlib.h>
+
 #include <string>
 
 #include "gemm_epi.cuh"
@@ -16,23 +18,26 @@
 namespace bd {
 
 bool get_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t bc, uint32_t br);
+bool get_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t bc, uint32_t br, uint32_t esz);
 
-template <int BN>
+// TMAOUT: the epilogue leaves through TMA stores (gemm_epilogue_tile_tma) and double-buffers its 4 KB staging boxes
+template <int BN, bool TMAOUT>
 struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NSTAGE = 6;
-  static constexpr int STAGING_BYTES = N_EPI_WARPS * 32 * 32 * 4;
+  static constexpr int NSTAGE = TMAOUT ? 5 : 6;
+  static constexpr int STAGING_BYTES = N_EPI_WARPS * 32 * 32 * 4 * (TMAOUT ? 2 : 1);
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 512;
 };
 
-template <int BN, int EPI, int HD>
+template <int BN, int EPI, int HD, bool TMAOUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
-  using Cfg = Gemm2Cfg<BN>;
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmOut, const GemmArgs args) {
+  using Cfg = Gemm2Cfg<BN, TMAOUT>;
   constexpr int NSTAGE = Cfg::NSTAGE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -132,7 +137,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int ew = warp - EPI_WARP0;
     const int quad = warp & 3;
     const int grp = ew >> 2;
-    uint32_t* tile_s = staging + ew * 1024;
+    uint32_t* tile_s = staging + ew * (TMAOUT ? 2048 : 1024);
+    uint32_t sbuf_sel = 0;
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
       const int acc = it & 1;
@@ -142,7 +148,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
-      gemm_epilogue_tile<BN, EPI, HD>(args, tile_s, t_acc, row_w, n_blk, lane, grp);
+      if constexpr (TMAOUT) {
+        gemm_epilogue_tile_tma<BN, EPI>(args, &tmOut, reinterpret_cast<uint8_t*>(tile_s), sbuf_sel, t_acc, row_w, n_blk, lane, grp);
+      } else {
+        gemm_epilogue_tile<BN, EPI, HD>(args, tile_s, t_acc, row_w, n_blk, lane, grp);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -150,6 +160,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
       }
     }
+    if (TMAOUT && lane == 0) bulk_wait_group_read<0>();  // staging boxes stay valid until the last store has read them
   }
 
   tc_fence_before();
@@ -164,13 +175,19 @@ static int g_num_sms2 = 0;
 extern thread_local std::string g_tc_err_2;
 thread_local std::string g_tc_err_2;
 
-template <int BN, int EPI, int HD>
+template <int BN, int EPI, int HD, bool TMAOUT>
 static cudaError_t launch2(const bf16* A, const bf16* W, int M, int N, int K, const GemmEpi& e, cudaStream_t s) {
-  using Cfg = Gemm2Cfg<BN>;
-  CUtensorMap tmA, tmB;
+  using Cfg = Gemm2Cfg<BN, TMAOUT>;
+  CUtensorMap tmA, tmB, tmOut;
   if (!get_tmap_2d_bf16(&tmA, A, M, K, K, BK, BM)) return cudaErrorInvalidValue;
   if (!get_tmap_2d_bf16(&tmB, W, N, K, K, BK, BN / 2)) return cudaErrorInvalidValue;
-  auto kern = gemm_tc2_kernel<BN, EPI, HD>;
+  tmOut = tmA;
+  if (TMAOUT) {
+    const bool ok = (EPI == EPI_RESID) ? get_tmap_2d(&tmOut, e.out_f32, M, N, e.ldo, 32, 32, 4)
+                                       : get_tmap_2d(&tmOut, e.out_act, M, N, N, 64, 32, 2);
+    if (!ok) return cudaErrorInvalidValue;
+  }
+  auto kern = gemm_tc2_kernel<BN, EPI, HD, TMAOUT>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -186,21 +203,27 @@ static cudaError_t launch2(const bf16* A, const bf16* W, int M, int N, int K, co
   const int max_pairs = g_num_sms2 / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   GemmArgs args{M, N, K, e};
-  kern<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, args);
+  kern<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, tmOut, args);
   return cudaGetLastError();
 }
 
 cudaError_t gemm_tc_pair(const bf16* A, const bf16* W, int M, int N, int K, int epi, const GemmEpi& e, cudaStream_t s) {
   if (M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0 || (N % 4) != 0) return cudaErrorInvalidValue;
+  const char* tv = getenv("BD_GEMM_TMA_EPI");   // debug switch: 0 = register/LSU epilogue everywhere
+  const bool tma_out = (N % 64) == 0 && !(tv && atoi(tv) == 0);
   switch (epi) {
-    case EPI_F32: return launch2<256, EPI_F32, 32>(A, W, M, N, K, e, s);
-    case EPI_RESID: return launch2<256, EPI_RESID, 32>(A, W, M, N, K, e, s);
-    case EPI_GELU: return launch2<256, EPI_GELU, 32>(A, W, M, N, K, e, s);
-    case EPI_ACT: return launch2<256, EPI_ACT, 32>(A, W, M, N, K, e, s);
+    case EPI_F32: return launch2<256, EPI_F32, 32, false>(A, W, M, N, K, e, s);
+    case EPI_RESID:
+      return tma_out && (e.ldo % 4) == 0 ? launch2<256, EPI_RESID, 32, true>(A, W, M, N, K, e, s)
+                                         : launch2<256, EPI_RESID, 32, false>(A, W, M, N, K, e, s);
+    case EPI_GELU:
+      return tma_out ? launch2<256, EPI_GELU, 32, true>(A, W, M, N, K, e, s) : launch2<256, EPI_GELU, 32, false>(A, W, M, N, K, e, s);
+    case EPI_ACT:
+      return tma_out ? launch2<256, EPI_ACT, 32, true>(A, W, M, N, K, e, s) : launch2<256, EPI_ACT, 32, false>(A, W, M, N, K, e, s);
     case EPI_QKV:
       if (N != 3 * e.heads * e.head_dim || (e.heads * e.head_dim) % 192 != 0) return cudaErrorInvalidValue;
-      if (e.head_dim == 96) return launch2<192, EPI_QKV, 96>(A, W, M, N, K, e, s);
-      if (e.head_dim == 64) return launch2<192, EPI_QKV, 64>(A, W, M, N, K, e, s);
+      if (e.head_dim == 96) return launch2<192, EPI_QKV, 96, false>(A, W, M, N, K, e, s);
+      if (e.head_dim == 64) return launch2<192, EPI_QKV, 64, false>(A, W, M, N, K, e, s);
       return cudaErrorInvalidValue;
   }
   return cudaErrorInvalidValue;

@@ -646,6 +646,7 @@ static cudaError_t launch_prefix(const bf16* Q, const bf16* K, const bf16* Vt, b
   if (nrows > 8 || nrows < 1 || seq > PFX_MAXSEQ) return cudaErrorInvalidValue;
   const float sl = scale * 1.4426950408889634f;
   const int grid = L * heads;
+  note_extra_launches(1);
   switch (nrows) {
     case 1: attention_prefix_rows_kernel<HD, 1><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
     case 2: attention_prefix_rows_kernel<HD, 2><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;

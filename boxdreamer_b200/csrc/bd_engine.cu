@@ -93,7 +93,7 @@ static cudaEvent_t get_event(bd_engine* e) {
     bd_engine::Span _sp{(cat), nullptr, nullptr};                         \
     if (e->profile) { _sp.a = get_event(e); cudaEventRecord(_sp.a, s); }  \
     CK(expr);                                                             \
-    e->launches += (nk);                                                  \
+    e->launches += (nk) + take_extra_launches();                                                  \
     if (e->profile) { _sp.b = get_event(e); cudaEventRecord(_sp.b, s); e->spans.push_back(_sp); } \
   } while (0)
 

@@ -15,6 +15,7 @@ enum GemmEpiKind {
   EPI_RESID = 2,      // resid[M,N] (fp32) += gamma[N] * (acc + bias)   (gamma optional: DINOv2 LayerScale)
   EPI_QKV = 3,        // split q|k|v, per-head RMSNorm on q,k (optional), write Q,K [BH,seq_pad,hd] and V^T [BH,hd,seq_pad]
   EPI_ACT = 4,        // plain activation-dtype store
+  EPI_VT = 5,         // internal (gemm_tc2.cu): operands swapped, rows = v features, columns = tokens -> V^T [BH, hd, seq_pad]
 };
 
 struct GemmEpi {
@@ -47,6 +48,9 @@ cudaError_t attention_tc(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, 
 // v2: persistent, two query tiles per CTA in ping-pong, P in tensor memory (attn_tc2.cu); variant 2 of attention_tc
 cudaError_t attention_tc2(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int head_dim, int seq,
                           int seq_pad, float scale, cudaStream_t s);
+// launchers that enqueue more than one kernel report the extra ones here; the engine folds them into bd_launch_count()
+void note_extra_launches(int n);
+int take_extra_launches();
 void tc_set_num_sms(int n);
 const char* tc_last_error();
 

@@ -28,6 +28,8 @@ struct GemmCfg {
 struct GemmArgs {
   int M, N, K;
   GemmEpi e;
+  int qkv_col_base = 0;  // EPI_QKV on a column slice of the q|k|v weight: global column of this GEMM's column 0
+  int m_fastest = 0;  // tile order: consecutive tiles walk M (swapped-operand V^T GEMM: the token block is shared)
 };
 
 __device__ __forceinline__ float gelu_erf_fast(float x) {
@@ -195,8 +197,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_
     for (int u = grp; u < UNITS; u += 2) {
       const int col0 = n_blk * BN + u * HD;
       if (col0 >= N) continue;
-      const int which = col0 / d_model;            // 0 q, 1 k, 2 v
-      const int head = (col0 % d_model) / HD;
+      const int which = (args.qkv_col_base + col0) / d_model;            // 0 q, 1 k, 2 v
+      const int head = ((args.qkv_col_base + col0) % d_model) / HD;
       float f[HD];
 #pragma unroll
       for (int c = 0; c < HD / 32; ++c) {
@@ -318,6 +320,140 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmArgs& args, con
     if (lane == 0) {
       if constexpr (EPI == EPI_RESID) tma_reduce_add_2d(tm_out, sb, col0, row_w);
       else tma_store_2d(tm_out, sb, col0, row_w);
+      bulk_commit_group();
+    }
+    buf ^= 1;
+  }
+}
+
+// q|k projection epilogue through TMA (CTA-pair kernel): per head, bias (+ RMSNorm over the head) in registers, then
+// HD/32 staging boxes of 32 rows x 32 bf16 (64-byte rows, 64B swizzle) stored into Q or K [L*heads, seq(_pad), HD].
+// A 32-row slab that crosses an image boundary (or the end of M) cannot be a TMA box (negative start coordinates fault
+// on the device), so those slabs -- 1 in 8 for DINOv2's 261 tokens, none for the decoder -- store their rows directly,
+// 4 x 16 bytes per lane and piece.  Pad rows are never written.  sbuf: this warp's four 2 KB boxes.
+template <int BN, int HD>
+__device__ __forceinline__ void gemm_epilogue_qk_tma(const GemmArgs& args, const CUtensorMap* tm_q, const CUtensorMap* tm_k,
+                                                     uint8_t* sbuf, uint32_t& slot, uint32_t t_acc, int row_w, int n_blk, int lane,
+                                                     int grp) {
+  static_assert(BN % HD == 0 && HD % 32 == 0, "BN must hold whole heads");
+  const GemmEpi& e = args.e;
+  if (row_w >= args.M) return;
+  constexpr int UNITS = BN / HD;
+  const int d_model = e.heads * HD;
+  const int l0 = row_w / e.seq, tok0 = row_w - l0 * e.seq;
+  const bool inside = tok0 + 32 <= e.seq;  // whole slab within one image (then also < M); warp-uniform
+  const int my_row = row_w + lane;
+  const int my_l = my_row / e.seq, my_tok = my_row - my_l * e.seq;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll 1
+  for (int u = grp; u < UNITS; u += 2) {
+    const int col0 = n_blk * BN + u * HD;
+    if (col0 >= args.N) continue;
+    const int which = col0 / d_model;  // 0 q, 1 k
+    const int head = (col0 - which * d_model) / HD;
+    float f[HD];
+    {
+      uint32_t v[HD];
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) tmem_ld_32x32b_x32p(t_acc + u * HD + c * 32, &v[c * 32]);
+      tmem_wait_ld();
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+      for (int j = 0; j < HD / 4; ++j) {
+        const float4 b = __ldg(b4 + j);
+        f[4 * j] = __uint_as_float(v[4 * j]) + b.x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+        f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+      }
+    }
+    const float* nw = (which == 0) ? e.q_norm_w : e.k_norm_w;
+    if (nw != nullptr) {
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < HD; ++j) ss = fmaf(f[j], f[j], ss);
+      const float r = rsqrtf(ss * (1.0f / HD) + e.rms_eps);
+      const float4* w4 = reinterpret_cast<const float4*>(nw);
+#pragma unroll
+      for (int j = 0; j < HD / 4; ++j) {
+        const float4 w = __ldg(w4 + j);
+        f[4 * j] = f[4 * j] * r * w.x; f[4 * j + 1] = f[4 * j + 1] * r * w.y;
+        f[4 * j + 2] = f[4 * j + 2] * r * w.z; f[4 * j + 3] = f[4 * j + 3] * r * w.w;
+      }
+    }
+    if (!inside) {
+      if (my_row < args.M) {
+        bf16* dst = reinterpret_cast<bf16*>(which == 0 ? e.q : e.k) +
+                    ((static_cast<long long>(my_l) * e.heads + head) * e.seq_pad + my_tok) * HD;
+#pragma unroll
+        for (int j = 0; j < HD / 8; ++j) {
+          const float* g = &f[8 * j];
+          reinterpret_cast<uint4*>(dst)[j] =
+              make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+        }
+      }
+      continue;
+    }
+    const CUtensorMap* tm = (which == 0) ? tm_q : tm_k;
+#pragma unroll
+    for (int p = 0; p < HD / 32; ++p) {
+      uint8_t* sb = sbuf + slot * 2048;
+      if (lane == 0) bulk_wait_group_read<3>();
+      __syncwarp();
+      uint4* row = reinterpret_cast<uint4*>(sb + lane * 64);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* g = &f[p * 32 + 8 * j];
+        row[j ^ sw] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(tm, sb, p * 32, tok0, l0 * e.heads + head);
+        bulk_commit_group();
+      }
+      slot = (slot + 1) & 3;
+    }
+  }
+}
+
+// V^T epilogue of the swapped-operand GEMM (rows = v features, columns = tokens): lane = one feature row, 64 tokens per
+// 128-byte staging row, stored into V^T viewed as [L, d_model, seq(_pad)].  The innermost (token) coordinate of a TMA
+// store must be 16-byte aligned and chunks must not cross images, so the dispatcher takes this path only for
+// seq % 64 == 0 (the decoder); otherwise V goes through the row-major epilogue's strided V^T stores.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_vt_tma(const GemmArgs& args, const CUtensorMap* tm_v, uint8_t* sbuf, uint32_t& buf,
+                                                     uint32_t t_acc, int row_w, int n_blk, int lane, int grp) {
+  const GemmEpi& e = args.e;
+  if (row_w >= args.M) return;
+  const float b = (row_w + lane < args.M) ? __ldg(e.bias + row_w + lane) : 0.f;
+  const int sw = lane & 7;
+  constexpr int NCH = (BN / 2) / 64;
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    const int colt = grp * (BN / 2) + c * 64;
+    const int n0 = n_blk * BN + colt;  // first token of the chunk (global index l * seq + tok)
+    if (n0 >= args.N) continue;
+    uint8_t* sb = sbuf + buf * 4096;
+    if (lane == 0) bulk_wait_group_read<1>();
+    __syncwarp();
+    uint4* row = reinterpret_cast<uint4*>(sb + lane * 128);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(t_acc + colt + h * 32, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        row[(h * 4 + j) ^ sw] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * j]) + b, __uint_as_float(v[8 * j + 1]) + b),
+                                           pack_bf16x2(__uint_as_float(v[8 * j + 2]) + b, __uint_as_float(v[8 * j + 3]) + b),
+                                           pack_bf16x2(__uint_as_float(v[8 * j + 4]) + b, __uint_as_float(v[8 * j + 5]) + b),
+                                           pack_bf16x2(__uint_as_float(v[8 * j + 6]) + b, __uint_as_float(v[8 * j + 7]) + b));
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      const int l = n0 / e.seq;
+      tma_store_3d(tm_v, sb, n0 - l * e.seq, row_w, l);
       bulk_commit_group();
     }
     buf ^= 1;

@@ -159,6 +159,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 static thread_local std::string g_tc_err;
 const char* tc_last_error() { return g_tc_err.c_str(); }
+static thread_local int g_extra_launches = 0;
+void note_extra_launches(int n) { g_extra_launches += n; }
+int take_extra_launches() { const int n = g_extra_launches; g_extra_launches = 0; return n; }
 static int g_num_sms = 0;
 void tc_set_num_sms(int n) { g_num_sms = n; }
 
@@ -223,6 +226,48 @@ bool get_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols
 }
 bool get_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t bc, uint32_t br) {
   return get_tmap_2d(out, ptr, rows, cols, pitch, bc, br, 2);
+}
+
+// 3D bf16 tensor (d0 contiguous; d1, d2 with byte strides s1, s2), box {b0, b1, 1}; swizzle span = b0 * 2 bytes (64 or 128).
+// Used by the q|k|v^T epilogue stores, which rely on the map clipping d1 at the unpadded sequence length.
+struct Tmap3Key {
+  const void* p; uint64_t d0, d1, d2, s1, s2; uint32_t b0, b1;
+  bool operator==(const Tmap3Key& o) const {
+    return p == o.p && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s1 == o.s1 && s2 == o.s2 && b0 == o.b0 && b1 == o.b1;
+  }
+};
+struct Tmap3Hash {
+  size_t operator()(const Tmap3Key& k) const {
+    size_t h = reinterpret_cast<size_t>(k.p);
+    h = h * 1000003u ^ k.d0; h = h * 1000003u ^ k.d1; h = h * 1000003u ^ k.d2; h = h * 1000003u ^ k.s1; h = h * 1000003u ^ k.s2;
+    h = h * 1000003u ^ k.b0; h = h * 1000003u ^ k.b1;
+    return h;
+  }
+};
+static std::unordered_map<Tmap3Key, CUtensorMap, Tmap3Hash> g_tmaps3;
+
+bool get_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2, uint32_t b0,
+                      uint32_t b1) {
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  Tmap3Key k{ptr, d0, d1, d2, s1, s2, b0, b1};
+  auto it = g_tmaps3.find(k);
+  if (it != g_tmaps3.end()) { *out = it->second; return true; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { g_tc_err = "cuTensorMapEncodeTiled entry point unavailable"; return false; }
+  const CUtensorMapSwizzle swz = (b0 * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : (b0 * 2 == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstride[2] = {s1, s2};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_tc_err = "cuTensorMapEncodeTiled (3d) failed, code " + std::to_string(static_cast<int>(r));
+    return false;
+  }
+  g_tmaps3.emplace(k, *out);
+  return true;
 }
 
 template <int BN, int EPI, int HD>

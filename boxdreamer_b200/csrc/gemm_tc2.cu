@@ -19,6 +19,8 @@ namespace bd {
 
 bool get_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t bc, uint32_t br);
 bool get_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t bc, uint32_t br, uint32_t esz);
+bool get_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2, uint32_t b0,
+                      uint32_t b1);
 
 // TMAOUT: the epilogue leaves through TMA stores (gemm_epilogue_tile_tma) and double-buffers its 4 KB staging boxes
 template <int BN, bool TMAOUT>
@@ -36,7 +38,7 @@ struct Gemm2Cfg {
 template <int BN, int EPI, int HD, bool TMAOUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmOut, const GemmArgs args) {
+                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2, const GemmArgs args) {
   using Cfg = Gemm2Cfg<BN, TMAOUT>;
   constexpr int NSTAGE = Cfg::NSTAGE;
   extern __shared__ uint8_t smem_raw[];
@@ -90,7 +92,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = pair; tile < num_tiles; tile += npairs) {
-      const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+      const int m_blk = args.m_fastest ? tile % tiles_m : tile / tiles_n;
+      const int n_blk = args.m_fastest ? tile / tiles_m : tile % tiles_n;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
@@ -143,12 +146,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+      const int m_blk = args.m_fastest ? tile % tiles_m : tile / tiles_n;
+      const int n_blk = args.m_fastest ? tile / tiles_m : tile % tiles_n;
       const int row_w = m_blk * 2 * BM + static_cast<int>(rank) * BM + quad * 32;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
-      if constexpr (TMAOUT) {
+      if constexpr (TMAOUT && EPI == EPI_QKV) {
+        gemm_epilogue_qk_tma<BN, HD>(args, &tmOut, &tmOut2, reinterpret_cast<uint8_t*>(tile_s), sbuf_sel, t_acc, row_w, n_blk, lane, grp);
+      } else if constexpr (TMAOUT && EPI == EPI_VT) {
+        gemm_epilogue_vt_tma<BN>(args, &tmOut, reinterpret_cast<uint8_t*>(tile_s), sbuf_sel, t_acc, row_w, n_blk, lane, grp);
+      } else if constexpr (TMAOUT) {
         gemm_epilogue_tile_tma<BN, EPI>(args, &tmOut, reinterpret_cast<uint8_t*>(tile_s), sbuf_sel, t_acc, row_w, n_blk, lane, grp);
       } else {
         gemm_epilogue_tile<BN, EPI, HD>(args, tile_s, t_acc, row_w, n_blk, lane, grp);
@@ -176,15 +184,29 @@ extern thread_local std::string g_tc_err_2;
 thread_local std::string g_tc_err_2;
 
 template <int BN, int EPI, int HD, bool TMAOUT>
-static cudaError_t launch2(const bf16* A, const bf16* W, int M, int N, int K, const GemmEpi& e, cudaStream_t s) {
+static cudaError_t launch2(const bf16* A, const bf16* W, int M, int N, int K, const GemmEpi& e, cudaStream_t s, int col_base = 0) {
   using Cfg = Gemm2Cfg<BN, TMAOUT>;
   CUtensorMap tmA, tmB, tmOut;
   if (!get_tmap_2d_bf16(&tmA, A, M, K, K, BK, BM)) return cudaErrorInvalidValue;
   if (!get_tmap_2d_bf16(&tmB, W, N, K, K, BK, BN / 2)) return cudaErrorInvalidValue;
   tmOut = tmA;
+  CUtensorMap tmOut2 = tmA;
+  bool m_fastest = false;
   if (TMAOUT) {
-    const bool ok = (EPI == EPI_RESID) ? get_tmap_2d(&tmOut, e.out_f32, M, N, e.ldo, 32, 32, 4)
-                                       : get_tmap_2d(&tmOut, e.out_act, M, N, N, 64, 32, 2);
+    bool ok;
+    if (EPI == EPI_QKV) {  // rows = tokens (M = L * seq), q | k columns only
+      const uint64_t lh = static_cast<uint64_t>(M / e.seq) * e.heads;
+      ok = get_tmap_3d_bf16(&tmOut, e.q, HD, e.seq, lh, HD * 2, static_cast<uint64_t>(e.seq_pad) * HD * 2, 32, 32) &&
+           get_tmap_3d_bf16(&tmOut2, e.k, HD, e.seq, lh, HD * 2, static_cast<uint64_t>(e.seq_pad) * HD * 2, 32, 32);
+    } else if (EPI == EPI_VT) {  // rows = v features (M = d_model), columns = tokens (N = L * seq)
+      ok = get_tmap_3d_bf16(&tmOut, e.v, e.seq, M, N / e.seq, static_cast<uint64_t>(e.seq_pad) * 2,
+                            static_cast<uint64_t>(M) * e.seq_pad * 2, 64, 32);
+      m_fastest = true;
+    } else if (EPI == EPI_RESID) {
+      ok = get_tmap_2d(&tmOut, e.out_f32, M, N, e.ldo, 32, 32, 4);
+    } else {
+      ok = get_tmap_2d(&tmOut, e.out_act, M, N, N, 64, 32, 2);
+    }
     if (!ok) return cudaErrorInvalidValue;
   }
   auto kern = gemm_tc2_kernel<BN, EPI, HD, TMAOUT>;
@@ -202,8 +224,8 @@ static cudaError_t launch2(const bf16* A, const bf16* W, int M, int N, int K, co
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   const int max_pairs = g_num_sms2 / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  GemmArgs args{M, N, K, e};
-  kern<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, tmOut, args);
+  GemmArgs args{M, N, K, e, col_base, m_fastest ? 1 : 0};
+  kern<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, tmOut, tmOut2, args);
   return cudaGetLastError();
 }
 
@@ -222,6 +244,22 @@ cudaError_t gemm_tc_pair(const bf16* A, const bf16* W, int M, int N, int K, int 
       return tma_out ? launch2<256, EPI_ACT, 32, true>(A, W, M, N, K, e, s) : launch2<256, EPI_ACT, 32, false>(A, W, M, N, K, e, s);
     case EPI_QKV:
       if (N != 3 * e.heads * e.head_dim || (e.heads * e.head_dim) % 192 != 0) return cudaErrorInvalidValue;
+      if (!(tv && atoi(tv) == 0) && (M % e.seq) == 0 && (e.seq_pad % 8) == 0 && e.seq >= 32 && (e.head_dim == 96 || e.head_dim == 64)) {
+        // q|k: rows = tokens, per-head TMA stores.  v: for seq % 64 == 0 a second GEMM with the operands swapped
+        // (V^T = W_v . X^T: rows = features, columns = tokens) whose tiles are V^T boxes; otherwise the row-major
+        // epilogue on the v columns.
+        const int d_model = e.heads * e.head_dim;
+        cudaError_t err = e.head_dim == 96 ? launch2<192, EPI_QKV, 96, true>(A, W, M, 2 * d_model, K, e, s)
+                                           : launch2<256, EPI_QKV, 64, true>(A, W, M, 2 * d_model, K, e, s);
+        if (err != cudaSuccess) return err;
+        note_extra_launches(1);
+        GemmEpi ev = e;
+        ev.bias = e.bias + 2 * d_model;
+        const bf16* Wv = W + static_cast<size_t>(2) * d_model * K;
+        if ((e.seq % 64) == 0 && (d_model % 32) == 0) return launch2<256, EPI_VT, 32, true>(Wv, A, d_model, M, K, ev, s);
+        return e.head_dim == 96 ? launch2<192, EPI_QKV, 96, false>(A, Wv, M, d_model, K, ev, s, 2 * d_model)
+                                : launch2<192, EPI_QKV, 64, false>(A, Wv, M, d_model, K, ev, s, 2 * d_model);
+      }
       if (e.head_dim == 96) return launch2<192, EPI_QKV, 96, false>(A, W, M, N, K, e, s);
       if (e.head_dim == 64) return launch2<192, EPI_QKV, 64, false>(A, W, M, N, K, e, s);
       return cudaErrorInvalidValue;

@@ -4,7 +4,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from boxdreamer_b200 import _lib
 lib = _lib.load()
-L, heads, hd, seq = 64, 8, 96, 1536
+L, heads, hd, seq = (int(x) for x in (sys.argv[1:5] if len(sys.argv) >= 5 else (64, 8, 96, 1536)))
 seq_pad = (seq + 127) // 128 * 128
 Q = torch.randn(L * heads, seq_pad, hd, device="cuda").to(torch.bfloat16)
 K = torch.randn_like(Q)
@@ -22,7 +22,8 @@ torch.cuda.synchronize()
 lib.bd_debug_attention_trace(None)
 t = tr.cpu().view(3, 128, 4)
 t0 = int(t[t > 0].min())
-n_kv = 12
+bkv = 96 if hd == 96 else 128
+n_kv = (seq + bkv - 1) // bkv
 print("item j | MMA: waitP0 start/end, waitP1 start/end | SM0: wait start, S seen, ld done, arrive | SM1: ...   (cycles since first stamp)")
 for idx in range(2 * n_kv + 4):
     row = [int(x) - t0 if int(x) > 0 else -1 for x in t[:, idx, :].reshape(-1)]

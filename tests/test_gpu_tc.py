@@ -86,7 +86,8 @@ def _qkv_case(L, seq, heads, hd, norm, seed):
     return x, W, b, qw, kw, q, k, v, seq_pad
 
 
-@pytest.mark.parametrize("L,seq,heads,hd,norm", [(2, 512, 8, 96, True), (3, 261, 12, 64, False), (1, 1536, 8, 96, True)])
+@pytest.mark.parametrize("L,seq,heads,hd,norm", [(2, 512, 8, 96, True), (3, 261, 12, 64, False), (1, 1536, 8, 96, True), (2, 500, 8, 96, True),
+                                                 (2, 512, 12, 64, False), (3, 256, 12, 64, True), (1, 261, 12, 64, False)])
 def test_qkv_project_tc(lib, gemm_pair, L, seq, heads, hd, norm):
     x, W, b, qw, kw, q, k, v, seq_pad = _qkv_case(L, seq, heads, hd, norm, 17)
     Q = torch.zeros(L * heads, seq_pad, hd, device="cuda", dtype=torch.bfloat16)

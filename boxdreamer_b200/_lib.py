@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libboxdreamer_b200.so")
+LIB_PATH = os.environ.get("BD_LIB_PATH") or os.path.join(HERE, "libboxdreamer_b200.so")  # BD_LIB_PATH: A/B builds (scripts/build_variant.sh)
 
 BD_F32, BD_BF16 = 0, 1
 PRECISION_EXACT, PRECISION_BF16 = 0, 1

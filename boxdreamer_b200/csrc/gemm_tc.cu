@@ -35,7 +35,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty_bar = bars + 2 * NSTAGE + 2;  // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: role branches stay convergent, operands stay in uniform registers
   const int lane = threadIdx.x & 31;
   const int M = args.M, N = args.N, K = args.K;
   const int tiles_n = (N + BN - 1) / BN;

@@ -58,6 +58,14 @@ def gemm(M, N, K, epi):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "attn":   # attention only, current variant
+        print(json.dumps({
+            "attn_decoder_L64_h8_d96_N1536": attention(64, 8, 96, 1536, (2,)),
+            "attn_dino_L384_h12_d64_N261": attention(384, 12, 64, 261, (2,)),
+            "attn_long_L4_h8_d96_N9792": attention(4, 8, 96, 9792, (2,)),
+            "attn_336_L34_h12_d64_N581": attention(34, 12, 64, 581, (2,)),
+        }, indent=1))
+        sys.exit(0)
     res = {
         "attn_decoder_L64_h8_d96_N1536": attention(64, 8, 96, 1536),
         "attn_dino_L384_h12_d64_N261": attention(384, 12, 64, 261),

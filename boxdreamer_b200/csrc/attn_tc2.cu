@@ -34,32 +34,34 @@ static constexpr int A2_BQ = 128;
 template <int HD>
 struct Att2Cfg {
   static constexpr int BKV = (HD > 64) ? 96 : 128;   // keys per tile: S (BKV) + P (BKV/2) + O (HD) fp32 columns per query tile <= 256
-  static constexpr int NQS = (HD + 63) / 64;
-  static constexpr int Q_TILE = NQS * A2_BQ * 128;
-  static constexpr int K_SUB = BKV * 128;
-  static constexpr int K_TILE = NQS * K_SUB;
-  static constexpr int V_SUB = HD * 128;
-  static constexpr int V_TILE = 2 * V_SUB;            // always two 64-key boxes (the second one is half used when BKV = 96)
+  // Operand tiles are K-major.  Columns 0..63 live in SWIZZLE_128B boxes (128-byte rows); head dim 96 adds a 32-column
+  // SWIZZLE_64B box (64-byte rows) instead of a half-empty second 128-byte box, which is what makes room for two Q buffers.
+  static constexpr bool SPLIT = HD > 64;
+  static constexpr int Q_P0 = A2_BQ * 128, Q_P1 = SPLIT ? A2_BQ * 64 : 0, Q_TILE = Q_P0 + Q_P1;
+  static constexpr int K_P0 = BKV * 128, K_P1 = SPLIT ? BKV * 64 : 0, K_TILE = K_P0 + K_P1;
+  static constexpr bool VSPLIT = (BKV % 64) != 0;    // keys 64.. of a tile: a 32-key SWIZZLE_64B box (BKV 96) or a second 64-key box
+  static constexpr int V_P0 = HD * 128, V_P1 = VSPLIT ? HD * 64 : HD * 128, V_TILE = V_P0 + V_P1;
   static constexpr int NSTG = (HD > 64) ? 3 : 4;
-  static constexpr int QBUF = (HD > 64) ? 1 : 2;      // item-level Q buffering: the next item's Q is prefetched when smem allows
+  static constexpr int QBUF = 2;                      // the next item's Q is prefetched; the current one doubles as the O staging tile
   static constexpr int BAR_BYTES = 256 + 2048;       // mbarriers + 2 x 256 hand-over slots (a2_turn_*)
   static constexpr int SMEM_BYTES = QBUF * 2 * Q_TILE + NSTG * (K_TILE + V_TILE) + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 512;
   static constexpr int S_OFF = 0, P_OFF = BKV, O_OFF = BKV + BKV / 2;   // column offsets inside a tile's 256-column half
   static_assert(O_OFF + HD <= 256, "tile does not fit its TMEM half");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 struct Att2Args {
-  bf16* O;
   int heads, seq, seq_pad, BH;
   int q_off;         // first query row handled by this kernel (rows [0, q_off) are done by attention_prefix_rows)
   float scale_log2;
   long long* trace;  // debug: per-role clock64 stamps of CTA 0's first items (nullptr in production)
 };
+struct Att2Maps {    // Q, K: [BH*seq_pad, HD]; V^T: [BH*HD, seq_pad]; O: [L][seq][heads*HD] (3-D: rows are clipped at seq)
+  CUtensorMap q, q2, k, k2, v, v2, o, o2;   // *2: the 32-column (SWIZZLE_64B) boxes of head dim 96 / of 96-key tiles
+};
 #define A2_TRACE(role, slot) do { if (args.trace != nullptr && blockIdx.x == 0 && (slot) < 512) args.trace[(role) * 512 + (slot)] = clock64(); } while (0)
 
-// Named-barrier hand-over of the exp (MUFU) phase between the two softmax groups: group g waits for its turn, the
-// other group releases it.  Both calls count 256 threads (128 waiting + 128 arriving).
 // ptxas moves register-only work (the MUFU stream) freely across BAR instructions, so the hand-over is tied into the
 // data flow through shared memory: the exp loop's input offset is re-read (volatile) after the bar.sync, and the row sum
 // it produces is stored (volatile) before the bar.arrive.  One 4-byte slot per thread and direction.
@@ -70,37 +72,39 @@ __device__ __forceinline__ void a2_turn_wait(int g, float& dep, uint32_t slot) {
 __device__ __forceinline__ void a2_turn_pass(int g, float dep, uint32_t slot) {
   asm volatile("st.volatile.shared.f32 [%2], %0;\n\tbar.arrive %1, 256;" ::"f"(dep), "r"(2 + (g ^ 1)), "r"(slot) : "memory");
 }
+__device__ __forceinline__ void a2_group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(4 + g) : "memory"); }
 
 // S_g = Q_g K^T : HD/16 UMMAs (128 x ncols x 16), operands in shared memory (low descriptor words)
 template <int HD>
 __device__ __forceinline__ void a2_issue_s(uint32_t d_tmem, uint32_t q_lo, uint32_t k_lo, uint32_t idesc_s) {
   using Cfg = Att2Cfg<HD>;
 #pragma unroll
-  for (int k = 0; k < HD / 16; ++k)
-    umma_ss_lo_w(d_tmem, q_lo + (k / 4) * ((A2_BQ * 128) >> 4) + 2 * (k % 4), k_lo + (k / 4) * (Cfg::K_SUB >> 4) + 2 * (k % 4), idesc_s,
-                 k != 0 ? 1u : 0u);
+  for (int k = 0; k < HD / 16; ++k) {
+    if (k < 4) umma_ss_lh_w(d_tmem, q_lo + 2 * k, k_lo + 2 * k, SMEM_DESC_HI_SW128, idesc_s, k != 0 ? 1u : 0u);
+    else umma_ss_lh_w(d_tmem, q_lo + (Cfg::Q_P0 >> 4) + 2 * (k - 4), k_lo + (Cfg::K_P0 >> 4) + 2 * (k - 4), SMEM_DESC_HI_SW64, idesc_s, 1u);
+  }
 }
 // O_g (+)= P_g V : ncols/16 UMMAs (128 x HD x 16), P from tensor memory, V^T from shared memory
-template <int HD>
-__device__ __forceinline__ void a2_issue_pv(uint32_t d_tmem, uint32_t p_tmem, uint32_t v_lo, int ncols, uint32_t acc0) {
+template <int HD, bool CHECK>
+__device__ __forceinline__ void a2_issue_pv_k(uint32_t d_tmem, uint32_t p_tmem, uint32_t v_lo, int ncols, uint32_t acc0) {
   using Cfg = Att2Cfg<HD>;
   constexpr uint32_t idesc_o = make_idesc_bf16(A2_BQ, HD);
-  if (ncols == Cfg::BKV) {  // full tile: no per-step predicate, the UMMAs are issued back to back
-#pragma unroll
-    for (int k = 0; k < Cfg::BKV / 16; ++k)
-      umma_ts_lo_w(d_tmem, p_tmem + k * 8, v_lo + (k / 4) * (Cfg::V_SUB >> 4) + 2 * (k % 4), idesc_o, k == 0 ? acc0 : 1u);
-    return;
-  }
 #pragma unroll
   for (int k = 0; k < Cfg::BKV / 16; ++k) {
-    if (k * 16 < ncols) umma_ts_lo_w(d_tmem, p_tmem + k * 8, v_lo + (k / 4) * (Cfg::V_SUB >> 4) + 2 * (k % 4), idesc_o, k == 0 ? acc0 : 1u);
+    if (CHECK && k * 16 >= ncols) break;
+    if (k < 4) umma_ts_lh_w(d_tmem, p_tmem + k * 8, v_lo + 2 * k, SMEM_DESC_HI_SW128, idesc_o, k == 0 ? acc0 : 1u);
+    else umma_ts_lh_w(d_tmem, p_tmem + k * 8, v_lo + (Cfg::V_P0 >> 4) + 2 * (k - 4), Cfg::VSPLIT ? SMEM_DESC_HI_SW64 : SMEM_DESC_HI_SW128, idesc_o, 1u);
   }
+}
+template <int HD>
+__device__ __forceinline__ void a2_issue_pv(uint32_t d_tmem, uint32_t p_tmem, uint32_t v_lo, int ncols, uint32_t acc0) {
+  if (ncols == Att2Cfg<HD>::BKV) a2_issue_pv_k<HD, false>(d_tmem, p_tmem, v_lo, ncols, acc0);  // full tile: back-to-back UMMAs
+  else a2_issue_pv_k<HD, true>(d_tmem, p_tmem, v_lo, ncols, acc0);
 }
 
 template <int HD>
 __global__ void __launch_bounds__(A2_THREADS, 1)
-attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const Att2Args args) {
+attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
   using Cfg = Att2Cfg<HD>;
   constexpr int NSTG = Cfg::NSTG;
   constexpr int QBUF = Cfg::QBUF;
@@ -112,7 +116,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sV = sK + NSTG * Cfg::K_TILE;               // [NSTG][V_TILE]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NSTG * Cfg::V_TILE);
   uint64_t* q_full = bars;                  // [QBUF][2]
-  uint64_t* q_empty = bars + 4;             // [QBUF]
+  uint64_t* q_empty = bars + 4;             // [QBUF]  both softmax groups have stored their O tile out of this Q buffer
   uint64_t* k_full = bars + 6;              // [NSTG]
   uint64_t* k_empty = k_full + NSTG;
   uint64_t* v_full = k_empty + NSTG;
@@ -136,11 +140,18 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int tail_cols = (tail_keys + 15) & ~15;          // MMA N / K extent of the last tile
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tm.q);
+    tma_prefetch_desc(&tm.k);
+    tma_prefetch_desc(&tm.v);
+    tma_prefetch_desc(&tm.o);
+    if (Cfg::SPLIT) {
+      tma_prefetch_desc(&tm.q2);
+      tma_prefetch_desc(&tm.k2);
+      tma_prefetch_desc(&tm.o2);
+    }
+    tma_prefetch_desc(&tm.v2);
     for (int i = 0; i < 4; ++i) mbar_init(&q_full[i], 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&q_empty[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&q_empty[i], 2);
     for (int i = 0; i < NSTG; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -162,8 +173,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // broadcast through a shuffle so the compiler keeps the TMEM base (and everything derived from it) in uniform
-  // registers: otherwise every tcgen05.mma is wrapped in an R2UR "waterfall" loop that costs ~100 cycles per issue
+  // broadcast through a shuffle so the compiler keeps the TMEM base (and everything derived from it) in uniform registers
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
   // register budget: the two softmax warpgroups keep a whole S row per thread
@@ -171,132 +181,127 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == A2_CTRL_WARP) {
     // ===================== TMA producer (whole warp, elected lane issues) =====================
-    {
-      int st = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int bh = item / n_pairs, pair = item % n_pairs;
-        const int q0 = q_off + pair * 2 * A2_BQ;
-        const bool act1 = q0 + A2_BQ < seq;
-        const int qb = it % QBUF;
-        uint8_t* sQi = sQ + qb * 2 * Cfg::Q_TILE;
-        mbar_wait(&q_empty[qb], ((it / QBUF) & 1) ^ 1);  // the item that used this Q buffer has issued all its S MMAs
-        mbar_expect_tx_w(&q_full[qb * 2 + 0], Cfg::Q_TILE);
-#pragma unroll
-        for (int s = 0; s < Cfg::NQS; ++s) tma_load_2d_w(sQi + s * (A2_BQ * 128), &tmQ, &q_full[qb * 2 + 0], s * 64, bh * seq_pad + q0);
-        if (act1) {
-          mbar_expect_tx_w(&q_full[qb * 2 + 1], Cfg::Q_TILE);
-#pragma unroll
-          for (int s = 0; s < Cfg::NQS; ++s)
-            tma_load_2d_w(sQi + Cfg::Q_TILE + s * (A2_BQ * 128), &tmQ, &q_full[qb * 2 + 1], s * 64, bh * seq_pad + q0 + A2_BQ);
-        }
-        for (int j = 0; j < n_kv; ++j) {
-          mbar_wait(&k_empty[st], ph ^ 1);
-          mbar_expect_tx_w(&k_full[st], Cfg::K_TILE);
-#pragma unroll
-          for (int s = 0; s < Cfg::NQS; ++s)
-            tma_load_2d_w(sK + st * Cfg::K_TILE + s * Cfg::K_SUB, &tmK, &k_full[st], s * 64, bh * seq_pad + j * BKV);
-          mbar_wait(&v_empty[st], ph ^ 1);
-          mbar_expect_tx_w(&v_full[st], Cfg::V_TILE);
-#pragma unroll
-          for (int s = 0; s < 2; ++s)
-            tma_load_2d_w(sV + st * Cfg::V_TILE + s * Cfg::V_SUB, &tmV, &v_full[st], j * BKV + s * 64, bh * HD);
-          if (++st == NSTG) { st = 0; ph ^= 1; }
-        }
+    int st = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int bh = item / n_pairs, pair = item % n_pairs;
+      const int q0 = q_off + pair * 2 * A2_BQ;
+      const bool act1 = q0 + A2_BQ < seq;
+      const int qb = it % QBUF;
+      uint8_t* sQi = sQ + qb * 2 * Cfg::Q_TILE;
+      if (lane == 0) A2_TRACE(3, it * 8 + 0);
+      mbar_wait(&q_empty[qb], ((it / QBUF) & 1) ^ 1);  // the O tiles of the item that used this buffer have been stored
+      if (lane == 0) A2_TRACE(3, it * 8 + 1);
+      mbar_expect_tx_w(&q_full[qb * 2 + 0], Cfg::Q_TILE);
+      tma_load_2d_w(sQi, &tm.q, &q_full[qb * 2 + 0], 0, bh * seq_pad + q0);
+      if (Cfg::SPLIT) tma_load_2d_w(sQi + Cfg::Q_P0, &tm.q2, &q_full[qb * 2 + 0], 64, bh * seq_pad + q0);
+      if (act1) {
+        mbar_expect_tx_w(&q_full[qb * 2 + 1], Cfg::Q_TILE);
+        tma_load_2d_w(sQi + Cfg::Q_TILE, &tm.q, &q_full[qb * 2 + 1], 0, bh * seq_pad + q0 + A2_BQ);
+        if (Cfg::SPLIT) tma_load_2d_w(sQi + Cfg::Q_TILE + Cfg::Q_P0, &tm.q2, &q_full[qb * 2 + 1], 64, bh * seq_pad + q0 + A2_BQ);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx_w(&k_full[st], Cfg::K_TILE);
+        tma_load_2d_w(sK + st * Cfg::K_TILE, &tm.k, &k_full[st], 0, bh * seq_pad + j * BKV);
+        if (Cfg::SPLIT) tma_load_2d_w(sK + st * Cfg::K_TILE + Cfg::K_P0, &tm.k2, &k_full[st], 64, bh * seq_pad + j * BKV);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx_w(&v_full[st], Cfg::V_TILE);
+        tma_load_2d_w(sV + st * Cfg::V_TILE, &tm.v, &v_full[st], j * BKV, bh * HD);
+        tma_load_2d_w(sV + st * Cfg::V_TILE + Cfg::V_P0, &tm.v2, &v_full[st], j * BKV + 64, bh * HD);
+        if (++st == NSTG) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == A2_CTRL_WARP + 1) {
     // ===================== MMA issuer (whole warp, elected lane issues) =====================
-    {
-      int st = 0;
-      uint32_t ph = 0;
-      uint32_t pp0 = 0, pp1 = 0, fp0 = 0, fp1 = 0;   // parities of p_full[g] / s_free[g]
-      uint32_t q1p = 0;                              // bit qb: parity of q_full[qb][1] (only completes for items with an active second tile)
-      // every descriptor is  {low word, 0x40004040}:  the loop carries 32-bit low words derived from warp-uniform values
-      const uint32_t q_lo0 = make_smem_desc_lo(smem_u32(sQ)), k_lo0 = make_smem_desc_lo(smem_u32(sK)), v_lo0 = make_smem_desc_lo(smem_u32(sV));
-      constexpr uint32_t idesc_full = make_idesc_bf16(A2_BQ, BKV);
-      const uint32_t idesc_tail = make_idesc_bf16(A2_BQ, tail_cols);
-      const uint32_t tS0 = tmem_base + Cfg::S_OFF, tS1 = tmem_base + 256 + Cfg::S_OFF;
-      const uint32_t tP0 = tmem_base + Cfg::P_OFF, tP1 = tmem_base + 256 + Cfg::P_OFF;
-      const uint32_t tO0 = tmem_base + Cfg::O_OFF, tO1 = tmem_base + 256 + Cfg::O_OFF;
-      int it = 0;
+    int st = 0;
+    uint32_t ph = 0;
+    uint32_t pp0 = 0, pp1 = 0, fp0 = 0, fp1 = 0;   // parities of p_full[g] / s_free[g]
+    uint32_t q1p = 0;                              // bit qb: parity of q_full[qb][1] (only completes for items with an active second tile)
+    // every descriptor is {low word, constant high word}: the loop carries 32-bit low words derived from warp-uniform values
+    const uint32_t q_lo0 = make_smem_desc_lo(smem_u32(sQ)), k_lo0 = make_smem_desc_lo(smem_u32(sK)), v_lo0 = make_smem_desc_lo(smem_u32(sV));
+    constexpr uint32_t idesc_full = make_idesc_bf16(A2_BQ, BKV);
+    const uint32_t idesc_tail = make_idesc_bf16(A2_BQ, tail_cols);
+    const uint32_t tS0 = tmem_base + Cfg::S_OFF, tS1 = tmem_base + 256 + Cfg::S_OFF;
+    const uint32_t tP0 = tmem_base + Cfg::P_OFF, tP1 = tmem_base + 256 + Cfg::P_OFF;
+    const uint32_t tO0 = tmem_base + Cfg::O_OFF, tO1 = tmem_base + 256 + Cfg::O_OFF;
+    int it = 0;
 
-      // Issue order per item:  S0(0) S1(0) | for j: [S0(j+1) S1(j+1) as soon as the softmax groups hold S(j) in registers]
-      // PV0(j) PV1(j).  S(j+1) is therefore already complete when a group finishes tile j: the groups never wait for the
-      // tensor pipe in steady state and the kernel runs at the pace of the exp (MUFU) pipe.
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int pair = item % n_pairs;
-        const bool act1 = q_off + pair * 2 * A2_BQ + A2_BQ < seq;
-        const int qb = it % QBUF;
-        uint64_t* q_empty_i = &q_empty[qb];
-        const uint32_t q_lo = q_lo0 + qb * ((2 * Cfg::Q_TILE) >> 4);
-        const uint32_t q_lo1 = q_lo + (Cfg::Q_TILE >> 4);
-        mbar_wait(&q_full[qb * 2 + 0], (it / QBUF) & 1);
+    // Issue order per item:  S0(0) S1(0) | for j: [S0(j+1) S1(j+1) as soon as the softmax groups hold S(j) in registers]
+    // PV0(j) PV1(j).  S(j+1) is therefore already complete when a group finishes tile j: the groups never wait for the
+    // tensor pipe in steady state and the kernel runs at the pace of the exp (MUFU) pipe.
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int pair = item % n_pairs;
+      const bool act1 = q_off + pair * 2 * A2_BQ + A2_BQ < seq;
+      const int qb = it % QBUF;
+      const uint32_t q_lo = q_lo0 + qb * ((2 * Cfg::Q_TILE) >> 4);
+      const uint32_t q_lo1 = q_lo + (Cfg::Q_TILE >> 4);
+      if (lane == 0) A2_TRACE(3, it * 8 + 2);
+      mbar_wait(&q_full[qb * 2 + 0], (it / QBUF) & 1);
+      if (act1) {
+        mbar_wait(&q_full[qb * 2 + 1], (q1p >> qb) & 1);
+        q1p ^= 1u << qb;
+      }
+      if (lane == 0) A2_TRACE(3, it * 8 + 3);
+      mbar_wait(&k_full[st], ph);
+      if (lane == 0) A2_TRACE(3, it * 8 + 4);
+      tc_fence_after();
+      {
+        const uint32_t id0 = (n_kv == 1) ? idesc_tail : idesc_full;
+        const uint32_t k_lo = k_lo0 + st * (Cfg::K_TILE >> 4);
+        a2_issue_s<HD>(tS0, q_lo, k_lo, id0);
+        umma_commit_w(&s_full[0]);
         if (act1) {
-          mbar_wait(&q_full[qb * 2 + 1], (q1p >> qb) & 1);
-          q1p ^= 1u << qb;
+          a2_issue_s<HD>(tS1, q_lo1, k_lo, id0);
+          umma_commit_w(&s_full[1]);
         }
-        mbar_wait(&k_full[st], ph);
-        tc_fence_after();
-        {
-          const uint32_t id0 = (n_kv == 1) ? idesc_tail : idesc_full;
-          const uint32_t k_lo = k_lo0 + st * (Cfg::K_TILE >> 4);
-          a2_issue_s<HD>(tS0, q_lo, k_lo, id0);
+        umma_commit_w(&k_empty[st]);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int nc = (j == n_kv - 1) ? tail_cols : BKV;
+        const int st_next = (st + 1 == NSTG) ? 0 : st + 1;
+        const uint32_t ph_next = (st + 1 == NSTG) ? (ph ^ 1) : ph;
+        if (j + 1 < n_kv) {
+          const uint32_t idn = (j + 1 == n_kv - 1) ? idesc_tail : idesc_full;
+          const uint32_t k_lo = k_lo0 + st_next * (Cfg::K_TILE >> 4);
+          mbar_wait(&k_full[st_next], ph_next);
+          mbar_wait(&s_free[0], fp0);
+          fp0 ^= 1;
+          tc_fence_after();
+          a2_issue_s<HD>(tS0, q_lo, k_lo, idn);
           umma_commit_w(&s_full[0]);
           if (act1) {
-            a2_issue_s<HD>(tS1, q_lo1, k_lo, id0);
+            mbar_wait(&s_free[1], fp1);
+            fp1 ^= 1;
+            tc_fence_after();
+            a2_issue_s<HD>(tS1, q_lo1, k_lo, idn);
             umma_commit_w(&s_full[1]);
           }
-          umma_commit_w(&k_empty[st]);
-          if (n_kv == 1) umma_commit_w(q_empty_i);
+          umma_commit_w(&k_empty[st_next]);
         }
-        for (int j = 0; j < n_kv; ++j) {
-          const int nc = (j == n_kv - 1) ? tail_cols : BKV;
-          const int st_next = (st + 1 == NSTG) ? 0 : st + 1;
-          const uint32_t ph_next = (st + 1 == NSTG) ? (ph ^ 1) : ph;
-          if (j + 1 < n_kv) {
-            const uint32_t idn = (j + 1 == n_kv - 1) ? idesc_tail : idesc_full;
-            const uint32_t k_lo = k_lo0 + st_next * (Cfg::K_TILE >> 4);
-            mbar_wait(&k_full[st_next], ph_next);
-            mbar_wait(&s_free[0], fp0);
-            fp0 ^= 1;
-            tc_fence_after();
-            a2_issue_s<HD>(tS0, q_lo, k_lo, idn);
-            umma_commit_w(&s_full[0]);
-            if (act1) {
-              mbar_wait(&s_free[1], fp1);
-              fp1 ^= 1;
-              tc_fence_after();
-              a2_issue_s<HD>(tS1, q_lo1, k_lo, idn);
-              umma_commit_w(&s_full[1]);
-            }
-            umma_commit_w(&k_empty[st_next]);
-            if (j + 1 == n_kv - 1) umma_commit_w(q_empty_i);  // last S MMAs of this item issued
-          }
-          const uint32_t v_lo = v_lo0 + st * (Cfg::V_TILE >> 4);
-          const uint32_t acc0 = j == 0 ? 0u : 1u;
-          mbar_wait(&v_full[st], ph);
-          if (lane == 0) A2_TRACE(0, (it * n_kv + j) * 4 + 0);
-          mbar_wait(&p_full[0], pp0);
-          if (lane == 0) A2_TRACE(0, (it * n_kv + j) * 4 + 1);
-          pp0 ^= 1;
+        const uint32_t v_lo = v_lo0 + st * (Cfg::V_TILE >> 4);
+        const uint32_t acc0 = j == 0 ? 0u : 1u;
+        mbar_wait(&v_full[st], ph);
+        if (lane == 0) A2_TRACE(0, (it * n_kv + j) * 4 + 0);
+        mbar_wait(&p_full[0], pp0);
+        if (lane == 0) A2_TRACE(0, (it * n_kv + j) * 4 + 1);
+        pp0 ^= 1;
+        tc_fence_after();
+        a2_issue_pv<HD>(tO0, tP0, v_lo, nc, acc0);
+        umma_commit_w(&pv_done[0]);
+        if (act1) {
+          if (lane == 0) A2_TRACE(0, (it * n_kv + j) * 4 + 2);
+          mbar_wait(&p_full[1], pp1);
+          if (lane == 0) A2_TRACE(0, (it * n_kv + j) * 4 + 3);
+          pp1 ^= 1;
           tc_fence_after();
-          a2_issue_pv<HD>(tO0, tP0, v_lo, nc, acc0);
-          umma_commit_w(&pv_done[0]);
-          if (act1) {
-            if (lane == 0) A2_TRACE(0, (it * n_kv + j) * 4 + 2);
-            mbar_wait(&p_full[1], pp1);
-            if (lane == 0) A2_TRACE(0, (it * n_kv + j) * 4 + 3);
-            pp1 ^= 1;
-            tc_fence_after();
-            a2_issue_pv<HD>(tO1, tP1, v_lo, nc, acc0);
-            umma_commit_w(&pv_done[1]);
-          }
-          umma_commit_w(&v_empty[st]);
-          st = st_next;
-          ph = ph_next;
+          a2_issue_pv<HD>(tO1, tP1, v_lo, nc, acc0);
+          umma_commit_w(&pv_done[1]);
         }
+        umma_commit_w(&v_empty[st]);
+        st = st_next;
+        ph = ph_next;
       }
     }
   }
@@ -311,12 +316,23 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t t_p = tmem_base + lane_addr + g * 256 + Cfg::P_OFF;
     const uint32_t t_o = tmem_base + lane_addr + g * 256 + Cfg::O_OFF;
     const float c = args.scale_log2;
+    const bool storer = (quad == 0) && (lane == 0);   // issues this group's O stores and releases the Q buffer afterwards
     uint32_t s_cnt = 0, d_cnt = 0;
+    int pend_qb = -1, pend_arrivals = 0;    // O store in flight out of Q buffer pend_qb (storer thread only)
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int bh = item / n_pairs, pair = item % n_pairs;
       const int q0 = q_off + pair * 2 * A2_BQ + g * A2_BQ;
-      if (q0 >= seq) continue;  // inactive second tile: the whole group skips this item
+      if (q0 >= seq) {  // inactive second tile: the whole group skips this item (but still releases its last staging tile:
+                        // the producer may need that Q buffer before this group becomes active again)
+        if (storer && pend_qb >= 0) {
+          bulk_wait_group_read<0>();
+          for (int a = 0; a < pend_arrivals; ++a) mbar_arrive(&q_empty[pend_qb]);
+          pend_qb = -1;
+        }
+        continue;
+      }
+      const int qb = it % QBUF;
       // Anti-phase: while one group runs its exp loop (MUFU-bound) the other one reads S from TMEM, takes the row
       // maximum, stores P and hands it to the MMA warp.  Strict alternation g0, g1, g0, ... per key tile; group 1 opens
       // group 0's first turn of every item.  Items whose second tile is inactive run group 0 alone, without turns.
@@ -388,19 +404,15 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if constexpr (BKV == 128) tmem_st_32x32b_x32p(t_p + 32, sv + 32);
           else tmem_st_32x32b_x16(t_p + 32, sv + 32);
         } else {
-          // ---------- trimmed last tile: chunked, masked, two passes over TMEM ----------
-          const int nchunks = (tail_cols + 31) / 32;
+          // ---------- trimmed last tile: 16-column pieces, masked, two passes over TMEM ----------
+          const int n16 = tail_cols >> 4;
           float mx = -INFINITY;
-          for (int ch = 0; ch < nchunks; ++ch) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(t_s + ch * 32, v);
+          for (int c16 = 0; c16 < n16; ++c16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_s + c16 * 16, v);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float sc = __uint_as_float(v[i]);
-              if (kv0 + ch * 32 + i >= seq) sc = -INFINITY;
-              mx = fmaxf(mx, sc);
-            }
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (kv0 + c16 * 16 + i < seq) ? __uint_as_float(v[i]) : -INFINITY);
           }
           if (j == 0) {
             m_run = mx;
@@ -417,21 +429,21 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           float nmc = -m_run * c;
           float psum = 0.f;
           if (turns) a2_turn_wait(g, nmc, turn_slot);
-          for (int ch = 0; ch < nchunks; ++ch) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(t_s + ch * 32, v);
+          for (int c16 = 0; c16 < n16; ++c16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_s + c16 * 16, v);
             tmem_wait_ld();
-            uint32_t w[16];
+            uint32_t w[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < 8; ++i) {
               float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, nmc));
               float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, nmc));
-              if (kv0 + ch * 32 + 2 * i >= seq) p0 = 0.f;
-              if (kv0 + ch * 32 + 2 * i + 1 >= seq) p1 = 0.f;
+              if (kv0 + c16 * 16 + 2 * i >= seq) p0 = 0.f;
+              if (kv0 + c16 * 16 + 2 * i + 1 >= seq) p1 = 0.f;
               psum += p0 + p1;
               w[i] = pack_bf16x2(p0, p1);
             }
-            tmem_st_32x32b_x16(t_p + ch * 16, w);
+            tmem_st_32x32b_x8(t_p + c16 * 8, w);
           }
           l_run += psum;
           if (turns && g == 0) a2_turn_pass(g, l_run, turn_slot + 1024);  // the tail tile is always the last one (see the full-tile branch)
@@ -453,36 +465,52 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g]);
         if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 4 + 3);
+        // the previous item's O store has long finished reading its staging tile: release that Q buffer to the producer
+        if (storer && pend_qb >= 0) {
+          bulk_wait_group_read<0>();
+          for (int a = 0; a < pend_arrivals; ++a) mbar_arrive(&q_empty[pend_qb]);
+          pend_qb = -1;
+        }
       }
-      // ---- epilogue: O / l -> bf16, token-major ----
-      mbar_wait(&pv_done[g], d_cnt & 1);
+      // ---- epilogue: O / l -> bf16 into this tile's (dead) Q buffer in the TMA box layout, one bulk tensor store per box ----
+      mbar_wait(&pv_done[g], d_cnt & 1);    // also: every S MMA that read the Q tile has completed
       ++d_cnt;
       tc_fence_after();
+      if (g == 0 && quad == 0 && lane == 0) A2_TRACE(3, it * 8 + 5);
       const float inv_l = 1.0f / l_run;
-      const int row = q0 + r;
-      const int l_idx = bh / args.heads, head = bh % args.heads;
-      bf16* dst = args.O + (static_cast<long long>(l_idx) * seq + row) * (args.heads * HD) + head * HD;
+      uint8_t* stage = sQ + (qb * 2 + g) * Cfg::Q_TILE;
+      const uint32_t row0 = smem_u32(stage) + r * 128, row1 = smem_u32(stage) + Cfg::Q_P0 + r * 64;
 #pragma unroll
       for (int ch = 0; ch < HD / 32; ++ch) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_o + ch * 32, v);
         tmem_wait_ld();
-        if (row < seq) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]) * inv_l, __uint_as_float(v[8 * q + 1]) * inv_l);
-            o.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv_l, __uint_as_float(v[8 * q + 3]) * inv_l);
-            o.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv_l, __uint_as_float(v[8 * q + 5]) * inv_l);
-            o.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv_l, __uint_as_float(v[8 * q + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(dst + ch * 32 + q * 8) = o;
-          }
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t ox = pack_bf16x2(__uint_as_float(v[8 * q + 0]) * inv_l, __uint_as_float(v[8 * q + 1]) * inv_l);
+          const uint32_t oy = pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv_l, __uint_as_float(v[8 * q + 3]) * inv_l);
+          const uint32_t oz = pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv_l, __uint_as_float(v[8 * q + 5]) * inv_l);
+          const uint32_t ow = pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv_l, __uint_as_float(v[8 * q + 7]) * inv_l);
+          const int cch = ch * 4 + q;   // 16-byte chunk (8 columns) of the row
+          const uint32_t addr = (cch < 8) ? row0 + ((cch ^ (r & 7)) << 4) : row1 + (((cch - 8) ^ ((r >> 1) & 3)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ox), "r"(oy), "r"(oz), "r"(ow) : "memory");
         }
       }
       // O_g is free again once these loads completed; the next item's first PV_g is ordered behind this group's next
       // p_full arrival, which follows in program order.
       tc_fence_before();
+      fence_proxy_async_smem();
+      a2_group_sync(g);
+      if (storer) {
+        const int l_idx = bh / args.heads, head = bh % args.heads;
+        tma_store_3d(&tm.o, stage, head * HD, q0, l_idx);
+        if (Cfg::SPLIT) tma_store_3d(&tm.o2, stage + Cfg::Q_P0, head * HD + 64, q0, l_idx);
+        bulk_commit_group();
+        pend_qb = qb;
+        pend_arrivals = (g == 0 && !turns) ? 2 : 1;   // group 0 also arrives for an inactive group 1
+      }
     }
+    if (storer && pend_qb >= 0) bulk_wait_group<0>();   // the last store must be complete before the CTA's shared memory goes away
   }
 
   tc_fence_before();
@@ -497,15 +525,29 @@ static int g_att2_sms = 0;
 static long long* g_att2_trace = nullptr;
 void attention_tc2_set_trace(long long* dev_buf) { g_att2_trace = dev_buf; }
 
+bool get_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2, uint32_t b0,
+                      uint32_t b1);
+
 template <int HD>
 static cudaError_t launch_att2(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int seq, int seq_pad,
                                float scale, int q_off, cudaStream_t s) {
   using Cfg = Att2Cfg<HD>;
   const int BH = L * heads;
-  CUtensorMap tq, tk, tv;
-  if (!get_tmap_2d_bf16(&tq, Q, static_cast<uint64_t>(BH) * seq_pad, HD, HD, 64, A2_BQ)) return cudaErrorInvalidValue;
-  if (!get_tmap_2d_bf16(&tk, K, static_cast<uint64_t>(BH) * seq_pad, HD, HD, 64, Cfg::BKV)) return cudaErrorInvalidValue;
-  if (!get_tmap_2d_bf16(&tv, Vt, static_cast<uint64_t>(BH) * HD, seq_pad, seq_pad, 64, HD)) return cudaErrorInvalidValue;
+  const uint64_t qk_rows = static_cast<uint64_t>(BH) * seq_pad, v_rows = static_cast<uint64_t>(BH) * HD;
+  const uint64_t o_cols = static_cast<uint64_t>(heads) * HD;
+  Att2Maps tm;
+  bool ok = get_tmap_2d_bf16(&tm.q, Q, qk_rows, HD, HD, 64, A2_BQ) && get_tmap_2d_bf16(&tm.k, K, qk_rows, HD, HD, 64, Cfg::BKV) &&
+            get_tmap_2d_bf16(&tm.v, Vt, v_rows, seq_pad, seq_pad, 64, HD) &&
+            get_tmap_3d_bf16(&tm.o, O, o_cols, seq, L, o_cols * 2, static_cast<uint64_t>(seq) * o_cols * 2, 64, A2_BQ);
+  if (ok && Cfg::SPLIT) {
+    ok = get_tmap_2d_bf16(&tm.q2, Q, qk_rows, HD, HD, 32, A2_BQ) && get_tmap_2d_bf16(&tm.k2, K, qk_rows, HD, HD, 32, Cfg::BKV) &&
+         get_tmap_3d_bf16(&tm.o2, O, o_cols, seq, L, o_cols * 2, static_cast<uint64_t>(seq) * o_cols * 2, 32, A2_BQ);
+  } else if (ok) {
+    tm.q2 = tm.q; tm.k2 = tm.k; tm.o2 = tm.o;
+  }
+  if (ok && Cfg::VSPLIT) ok = get_tmap_2d_bf16(&tm.v2, Vt, v_rows, seq_pad, seq_pad, 32, HD);
+  else if (ok) tm.v2 = tm.v;
+  if (!ok) return cudaErrorInvalidValue;
   auto kern = attn_tc2_kernel<HD>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -521,8 +563,8 @@ static cudaError_t launch_att2(const bf16* Q, const bf16* K, const bf16* Vt, bf1
   const int n_qt = (seq - q_off + A2_BQ - 1) / A2_BQ;
   const int n_items = BH * ((n_qt + 1) / 2);
   const int grid = n_items < g_att2_sms ? n_items : g_att2_sms;
-  Att2Args a{O, heads, seq, seq_pad, BH, q_off, scale * 1.4426950408889634f, g_att2_trace};
-  kern<<<grid, A2_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tk, tv, a);
+  Att2Args a{heads, seq, seq_pad, BH, q_off, scale * 1.4426950408889634f, g_att2_trace};
+  kern<<<grid, A2_THREADS, Cfg::SMEM_BYTES, s>>>(tm, a);
   return cudaGetLastError();
 }
 

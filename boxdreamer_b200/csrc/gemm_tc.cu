@@ -179,7 +179,8 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2D bf16 tensor [rows, cols] (cols contiguous, row pitch `pitch_elems`), box {box_cols, box_rows}, 128B swizzle, zero OOB fill.
+// 2D bf16 tensor [rows, cols] (cols contiguous, row pitch `pitch_elems`), box {box_cols, box_rows}, zero OOB fill; the swizzle
+// span equals the box row (128 bytes; 64 bytes for the 32-column boxes of the attention kernel's head-dim-96 operands).
 // esz = 2: bf16 elements, esz = 4: fp32 elements (epilogue TMA stores / reduce-adds).
 static bool make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_cols,
                          uint32_t box_rows, uint32_t esz) {
@@ -190,8 +191,8 @@ static bool make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint6
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols * esz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     g_tc_err = "cuTensorMapEncodeTiled failed, code " + std::to_string(static_cast<int>(r));
     return false;

@@ -15,12 +15,13 @@ def run():
 for _ in range(3):
     run()
 torch.cuda.synchronize()
-tr = torch.zeros(3 * 512, dtype=torch.int64, device="cuda")
+tr = torch.zeros(4 * 512, dtype=torch.int64, device="cuda")
 lib.bd_debug_attention_trace(_lib.ptr(tr))
 run()
 torch.cuda.synchronize()
 lib.bd_debug_attention_trace(None)
-t = tr.cpu().view(3, 128, 4)
+ev = tr.cpu()[3 * 512:].view(64, 8)
+t = tr.cpu()[:3 * 512].view(3, 128, 4)
 t0 = int(t[t > 0].min())
 bkv = 96 if hd == 96 else 128
 n_kv = (seq + bkv - 1) // bkv
@@ -29,3 +30,6 @@ for idx in range(2 * n_kv + 4):
     row = [int(x) - t0 if int(x) > 0 else -1 for x in t[:, idx, :].reshape(-1)]
     print(f"{idx // n_kv:2d} {idx % n_kv:2d} | " + " ".join(f"{v:7d}" for v in row[0:4]) + " | " + " ".join(f"{v:7d}" for v in row[4:8]) + " | " +
           " ".join(f"{v:7d}" for v in row[8:12]))
+print("item | producer: q_empty wait start / done | MMA: item start, q_full seen, k_full seen | softmax g0: last pv_done seen")
+for i in range(4):
+    print(f"{i:2d} | " + " ".join(f"{int(x) - t0 if int(x) > 0 else -1:7d}" for x in ev[i, :6]))

@@ -568,177 +568,129 @@ static cudaError_t launch_att2(const bf16* Q, const bf16* K, const bf16* Vt, bf1
   return cudaGetLastError();
 }
 
-// Rows [0, nrows) of every sequence on CUDA cores: one CTA per (l, h).  K and V^T are streamed once with 16-byte
-// loads (no staging); every thread folds its 8 keys / 8 dims into all nrows rows at once.  Used for the few tokens
-// (DINOv2: cls + 4 registers) that would otherwise cost a whole extra 128-row query tile.
-static constexpr int PFX_MAXSEQ = 640;
-
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
+// Rows [0, nrows) (nrows <= 8) of every sequence: one WARP per (image, head), flash-style over 96-key chunks with
+// warp-level mma.sync.m16n8k16 (the rows fill the upper half of the 16-row A fragment, the lower half is zero).  Used for
+// the few tokens (DINOv2: cls + 4 registers) that would otherwise cost a whole extra 128-row query tile.  K rows and V^T
+// rows are read straight from global memory into B fragments with 16- / 8-byte loads; this works because both
+// contractions are order-free, so the k slots of a fragment are mapped to whatever elements sit contiguously in memory:
+//   S = Q K^T : lane q (= lane % 4) covers dims [q*HD/4, (q+1)*HD/4): k-step s <- dims q*HD/4 + 4s .. +3
+//   O = P V   : score tile t (8 keys), column n holds key  16*(t/2) + 4*(n/2) + (n%2) + 2*(t%2),  so the four P values a
+//               lane feeds into PV k-step t/2 belong to the four consecutive keys 16*(t/2) + 4q .. +3 of V^T.
+// HBM/L2-bound: K and V^T of the (image, head) are streamed exactly once.
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int HD, int NR>
-__global__ void __launch_bounds__(256, 4) attention_prefix_rows_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K,
-                                                                    const bf16* __restrict__ Vt, bf16* __restrict__ O, int heads,
-                                                                    int seq, int seq_pad, float scale_log2) {
-  constexpr int nrows = NR;
-  __shared__ float sQ[NR][HD];
-  __shared__ __align__(16) float sS[NR][PFX_MAXSEQ + 8];
-  __shared__ float sO[NR][HD];
-  __shared__ float sInv[NR];
-  const int bh = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+static constexpr int PFX_WARPS = 4;       // warps (= (image, head) pairs) per CTA
+static constexpr int PFX_CHUNK_TILES = 12;  // 8-key score tiles per chunk (96 keys)
+
+template <int HD>
+__global__ void __launch_bounds__(PFX_WARPS * 32) attention_prefix_rows_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K,
+                                                                            const bf16* __restrict__ Vt, bf16* __restrict__ O, int BH,
+                                                                            int heads, int seq, int seq_pad, int nrows,
+                                                                            float scale_log2) {
+  constexpr int KS = HD / 16;          // k-steps of S = Q K^T
+  constexpr int DPL = HD / 4;          // dims per lane quarter
+  constexpr int NT = PFX_CHUNK_TILES;
+  constexpr int OT = HD / 8;           // 8-dim output tiles
+  const int lane = threadIdx.x & 31;
+  const int bh = blockIdx.x * PFX_WARPS + (threadIdx.x >> 5);
+  if (bh >= BH) return;
+  const int g = lane >> 2, q = lane & 3;
+  const bf16* Qb = Q + static_cast<long long>(bh) * seq_pad * HD;
   const bf16* Kb = K + static_cast<long long>(bh) * seq_pad * HD;
   const bf16* Vb = Vt + static_cast<long long>(bh) * HD * seq_pad;
-  const int nch_k = (seq + 7) / 8;  // 8-key chunks
-  for (int i = tid; i < nrows * HD; i += 256) {
-    sQ[i / HD][i % HD] = __bfloat162float(Q[(static_cast<long long>(bh) * seq_pad + i / HD) * HD + (i % HD)]);
-    sO[i / HD][i % HD] = 0.f;
+  // A fragments of Q (row g; rows 8..15 of the fragment are zero), pre-multiplied layout: a0 = dims +0,+1; a2 = dims +2,+3
+  uint32_t qa0[KS], qa2[KS];
+#pragma unroll
+  for (int s2 = 0; s2 < KS; ++s2) {
+    uint2 v = make_uint2(0u, 0u);
+    if (g < nrows) v = *reinterpret_cast<const uint2*>(Qb + static_cast<long long>(g) * HD + q * DPL + 4 * s2);
+    qa0[s2] = v.x;
+    qa2[s2] = v.y;
   }
-  for (int i = tid; i < nrows * (PFX_MAXSEQ + 8); i += 256) (&sS[0][0])[i] = 0.f;
-  __syncthreads();
-  // scores: work item = (key, 8-dim chunk); the CH chunks of a key sit in adjacent lanes
-  constexpr int CH = HD / 8;
-  const int n_items = (seq * CH + 255) / 256 * 256;  // whole warps take part in the shuffles
-  float qreg[NR][8];
-  {
-    const int chq = tid % CH;  // for CH == 8 every work item of this thread has the same chunk index
+  float o[OT][4];
 #pragma unroll
-    for (int r = 0; r < NR; ++r)
+  for (int t = 0; t < OT; ++t) { o[t][0] = o[t][1] = o[t][2] = o[t][3] = 0.f; }
+  float m_run = -INFINITY, l_run = 0.f;
+  const int n_chunks = (seq + NT * 8 - 1) / (NT * 8);
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int key0 = ch * NT * 8;
+    // ---- scores: NT tiles of 8 keys ----
+    float sc[NT][4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) qreg[r][i] = (r < nrows) ? sQ[r][chq * 8 + i] : 0.f;
-  }
-  for (int w0 = tid; w0 < n_items; w0 += 256 * 4) {   // 4 independent 16-byte loads in flight per thread
-    uint4 u[4];
+    for (int t = 0; t < NT; ++t) {
+      sc[t][0] = sc[t][1] = sc[t][2] = sc[t][3] = 0.f;
+      int key = key0 + 16 * (t >> 1) + 4 * (g >> 1) + (g & 1) + 2 * (t & 1);   // the key this lane's B fragment column (n = g) holds
+      key = key < seq_pad ? key : seq_pad - 1;
+      const bf16* kr = Kb + static_cast<long long>(key) * HD + q * DPL;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int w = w0 + b * 256;
-      const int key = w / CH, ch = w % CH;
-      u[b] = make_uint4(0u, 0u, 0u, 0u);
-      if (w < n_items && key < seq) u[b] = __ldg(reinterpret_cast<const uint4*>(Kb + static_cast<long long>(key) * HD + ch * 8));
-    }
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int w = w0 + b * 256;
-      if (w >= n_items) break;  // warp-uniform: n_items is a multiple of 256
-      const int key = w / CH, ch = w % CH;
-      float kf[8];
-      unpack8(u[b], kf);
-#pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        if (r >= nrows) break;
-        float acc = 0.f;
-        if constexpr (CH == 8) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc = fmaf(qreg[r][i], kf[i], acc);
-          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-          acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-          acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-          if (ch == 0 && key < seq) sS[r][key] = acc;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc = fmaf(sQ[r][ch * 8 + i], kf[i], acc);
-          if (key < seq) atomicAdd(&sS[r][key], acc);
-        }
+      for (int s2 = 0; s2 < KS; s2 += 2) {
+        const uint4 kv = __ldg(reinterpret_cast<const uint4*>(kr + 4 * s2));   // dims of k-steps s2, s2+1
+        mma_bf16_16816(sc[t], qa0[s2], 0u, qa2[s2], 0u, kv.x, kv.y);
+        mma_bf16_16816(sc[t], qa0[s2 + 1], 0u, qa2[s2 + 1], 0u, kv.z, kv.w);
       }
     }
-  }
-  __syncthreads();
-  if (warp < nrows) {
-    float* p = sS[warp];
+    // columns 2q, 2q+1 of tile t: keys key0 + 16*(t/2) + 4q + {0,1} + 2*(t%2); mask the tail
     float mx = -INFINITY;
-    for (int key = lane; key < seq; key += 32) mx = fmaxf(mx, p[key]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-    for (int key = lane; key < nch_k * 8; key += 32) {
-      float e = 0.f;
-      if (key < seq) {
-        e = exp2f((p[key] - mx) * scale_log2);
-        sum += e;
-        e = __bfloat162float(__float2bfloat16_rn(e));  // P is bf16 on the tensor path too
-      }
-      p[key] = e;
+    for (int t = 0; t < NT; ++t) {
+      const int kk = key0 + 16 * (t >> 1) + 4 * q + 2 * (t & 1);
+      if (kk >= seq) sc[t][0] = -INFINITY;
+      if (kk + 1 >= seq) sc[t][1] = -INFINITY;
+      mx = fmaxf(mx, fmaxf(sc[t][0], sc[t][1]));
     }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float m_new = fmaxf(m_run, mx);          // chunk 0 always holds valid keys, so m_new is finite
+    const float alpha = exp2f((m_run - m_new) * scale_log2);
+    m_run = m_new;
+    const float nmc = -m_new * scale_log2;
+    float psum = 0.f;
+    uint32_t pa[NT];   // bf16 pairs (row g): tile t -> keys of k-slot pair
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) sInv[warp] = 1.0f / sum;
-  }
-  __syncthreads();
-  // P V: 4 lanes per output dim split the 8-key chunks, registers accumulate all rows, one shuffle reduction at the end
-  for (int d0 = 0; d0 < HD; d0 += 64) {
-    const int dcol = d0 + (tid >> 2), part = tid & 3;
-    float acc[NR];
+    for (int t = 0; t < NT; ++t) {
+      const float p0 = exp2f(fmaf(sc[t][0], scale_log2, nmc));
+      const float p1 = exp2f(fmaf(sc[t][1], scale_log2, nmc));
+      psum += p0 + p1;
+      pa[t] = pack_bf16x2(p0, p1);
+    }
+    psum += __shfl_xor_sync(0xffffffffu, psum, 1);
+    psum += __shfl_xor_sync(0xffffffffu, psum, 2);
+    l_run = l_run * alpha + psum;
 #pragma unroll
-    for (int r = 0; r < NR; ++r) acc[r] = 0.f;
-    if (dcol < HD) {
-      for (int c0 = part; c0 < nch_k; c0 += 16) {   // 4 independent 16-byte loads in flight per thread
-        uint4 u[4];
+    for (int t = 0; t < OT; ++t) { o[t][0] *= alpha; o[t][1] *= alpha; }
+    // ---- O += P V : k-step T = tiles 2T, 2T+1 = keys key0 + 16T + 4q .. +3 (one 8-byte load of V^T per output tile) ----
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int c = c0 + 4 * b;
-          u[b] = make_uint4(0u, 0u, 0u, 0u);
-          if (c < nch_k) u[b] = __ldg(reinterpret_cast<const uint4*>(Vb + static_cast<long long>(dcol) * seq_pad + c * 8));
-        }
+    for (int T2 = 0; T2 < NT / 2; ++T2) {
+      int kk = key0 + 16 * T2 + 4 * q;
+      kk = kk + 4 <= seq_pad ? kk : seq_pad - 4;    // (P is zero there)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int c = c0 + 4 * b;
-          if (c < nch_k) {
-            float vf[8];
-            unpack8(u[b], vf);
-#pragma unroll
-            for (int r = 0; r < NR; ++r) {
-              if (r < nrows) {
-                const float4 p0 = *reinterpret_cast<const float4*>(&sS[r][c * 8]);
-                const float4 p1 = *reinterpret_cast<const float4*>(&sS[r][c * 8 + 4]);
-                acc[r] = fmaf(p0.x, vf[0], acc[r]); acc[r] = fmaf(p0.y, vf[1], acc[r]);
-                acc[r] = fmaf(p0.z, vf[2], acc[r]); acc[r] = fmaf(p0.w, vf[3], acc[r]);
-                acc[r] = fmaf(p1.x, vf[4], acc[r]); acc[r] = fmaf(p1.y, vf[5], acc[r]);
-                acc[r] = fmaf(p1.z, vf[6], acc[r]); acc[r] = fmaf(p1.w, vf[7], acc[r]);
-              }
-            }
-          }
-        }
+      for (int t = 0; t < OT; ++t) {
+        const uint2 vv = __ldg(reinterpret_cast<const uint2*>(Vb + static_cast<long long>(8 * t + g) * seq_pad + kk));
+        mma_bf16_16816(o[t], pa[2 * T2], 0u, pa[2 * T2 + 1], 0u, vv.x, vv.y);
       }
     }
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
-      acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 2);
-      if (part == 0 && dcol < HD && r < nrows) sO[r][dcol] = acc[r];
-    }
   }
-  __syncthreads();
-  const int l_idx = bh / heads, head = bh % heads;
-  for (int i = tid; i < nrows * HD; i += 256) {
-    const int r = i / HD, dcol = i % HD;
-    O[(static_cast<long long>(l_idx) * seq + r) * (heads * HD) + head * HD + dcol] = __float2bfloat16_rn(sO[r][dcol] * sInv[r]);
+  if (g < nrows) {
+    const float inv = 1.0f / l_run;
+    const int l_idx = bh / heads, head = bh % heads;
+    bf16* dst = O + (static_cast<long long>(l_idx) * seq + g) * (heads * HD) + head * HD + 2 * q;
+#pragma unroll
+    for (int t = 0; t < OT; ++t) *reinterpret_cast<uint32_t*>(dst + 8 * t) = pack_bf16x2(o[t][0] * inv, o[t][1] * inv);
   }
 }
 
 template <int HD>
 static cudaError_t launch_prefix(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int seq, int seq_pad,
                                  int nrows, float scale, cudaStream_t s) {
-  if (nrows > 8 || nrows < 1 || seq > PFX_MAXSEQ) return cudaErrorInvalidValue;
+  if (nrows > 8 || nrows < 1 || seq_pad < 16) return cudaErrorInvalidValue;
   const float sl = scale * 1.4426950408889634f;
-  const int grid = L * heads;
+  const int BH = L * heads;
   note_extra_launches(1);
-  switch (nrows) {
-    case 1: attention_prefix_rows_kernel<HD, 1><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
-    case 2: attention_prefix_rows_kernel<HD, 2><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
-    case 3: attention_prefix_rows_kernel<HD, 3><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
-    case 4: attention_prefix_rows_kernel<HD, 4><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
-    case 5: attention_prefix_rows_kernel<HD, 5><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
-    case 6: attention_prefix_rows_kernel<HD, 6><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
-    case 7: attention_prefix_rows_kernel<HD, 7><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
-    default: attention_prefix_rows_kernel<HD, 8><<<grid, 256, 0, s>>>(Q, K, Vt, O, heads, seq, seq_pad, sl); break;
-  }
+  attention_prefix_rows_kernel<HD><<<(BH + PFX_WARPS - 1) / PFX_WARPS, PFX_WARPS * 32, 0, s>>>(Q, K, Vt, O, BH, heads, seq, seq_pad, nrows, sl);
   return cudaGetLastError();
 }
 
@@ -748,7 +700,7 @@ cudaError_t attention_tc2(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O,
   // a handful of rows beyond a multiple of 128 (DINOv2: 5 + 256) would cost a whole extra query tile: peel them off
   const int rem = seq % A2_BQ;
   static const bool no_peel = getenv("BD_ATT2_NOPEEL") != nullptr;  // debug switch
-  const int q_off = (!no_peel && rem > 0 && rem <= 8 && seq > A2_BQ && seq <= 640) ? rem : 0;
+  const int q_off = (!no_peel && rem > 0 && rem <= 8 && seq > A2_BQ) ? rem : 0;
   cudaError_t err;
   static const char* only = getenv("BD_ATT2_ONLY");  // debug switch: "prefix" or "main"
   if (only && only[0] == 'p') {

@@ -388,9 +388,12 @@ static int run_block(bd_engine* e, float* X, const std::string& p, int L, int se
   return BD_OK;
 }
 
-static int dino_forward_impl(bd_engine* e, const void* images, int dtype, float* feats_out, int L, cudaStream_t s) {
+// `out_img_off`: first image slot of feats_out / feats_act this call writes (the host-buffer entry runs the encoder in chunks
+// while later images are still in flight); feats_out may be null on the tensor path (only the bf16 copy is consumed then).
+static int dino_forward_impl(bd_engine* e, const void* images, int dtype, float* feats_out, int L, cudaStream_t s, int out_img_off = 0) {
   if (!e->finalized) return fail(BD_ERR_STATE, "weights not finalised (call bd_finalize_weights)");
-  if (L <= 0 || L > e->Lmax) return fail(BD_ERR_INVALID, "bd_dino_forward: L exceeds max_batch*max_views");
+  if (L <= 0 || out_img_off < 0 || out_img_off + L > e->Lmax) return fail(BD_ERR_INVALID, "bd_dino_forward: L exceeds max_batch*max_views");
+  if (!feats_out && !e->tc) return fail(BD_ERR_INVALID, "bd_dino_forward: null output");
   const int P = e->P, d = e->d;
   LAUNCH(BD_PROF_GLUE, 1, im2col_patches(images, dtype == BD_BF16, e->A_pe, e->tc, L, e->S, e->patch, e->kpe, s));
   GemmEpi pe;
@@ -407,8 +410,10 @@ static int dino_forward_impl(bd_engine* e, const void* images, int dtype, float*
     if (r != BD_OK) return r;
   }
   // final LayerNorm, patch tokens only (vision_transformer.py:263-267)
-  LAUNCH(BD_PROF_LAYERNORM, 1, layernorm(e->X_dino, WF(e, "dino.norm.weight"), WF(e, "dino.norm.bias"), 1e-6f, feats_out,
-                                         e->tc ? reinterpret_cast<bf16*>(e->feats_act) : nullptr, L * P, d, P, e->n_tok,
+  const size_t out_off = static_cast<size_t>(out_img_off) * P * d;
+  LAUNCH(BD_PROF_LAYERNORM, 1, layernorm(e->X_dino, WF(e, "dino.norm.weight"), WF(e, "dino.norm.bias"), 1e-6f,
+                                         feats_out ? feats_out + out_off : nullptr,
+                                         e->tc ? reinterpret_cast<bf16*>(e->feats_act) + out_off : nullptr, L * P, d, P, e->n_tok,
                                          e->n_prefix, s));
   return BD_OK;
 }
@@ -499,7 +504,7 @@ extern "C" int bd_forward(bd_handle e, const void* images, const void* bbox_feat
   if (B <= 0 || T <= 0 || B > e->Bmax || T > e->Tmax) return fail(BD_ERR_INVALID, "bd_forward: B/T exceed the workspace");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   float* heat = heat_out ? heat_out : e->heat;
-  int r = dino_forward_impl(e, images, in_dtype, e->feats, B * T, s);
+  int r = dino_forward_impl(e, images, in_dtype, e->tc ? nullptr : e->feats, B * T, s);
   if (r != BD_OK) return r;
   r = decoder_forward_impl(e, bbox_feat, in_dtype, e->feats, e->tc, query_idx, heat, nullptr, B, T, s);
   if (r != BD_OK) return r;
@@ -531,34 +536,46 @@ extern "C" int bd_forward_host(bd_handle e, const void* images_host, const void*
     CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&e->copy_ev[i], cudaEventDisableTiming));
   }
-  // The batch is processed in chunks of whole queries: chunk i+1's H2D (copy stream) overlaps chunk i's compute.
-  int nchunk = B >= 32 ? 2 : 1;
+  // Copy order = consumption order: the encoder only needs the images, so they go first, in `nchunk` pieces of whole queries
+  // (the first one small: its transfer is the only one nothing can hide); the reference heat maps (73 % of the bytes)
+  // follow and land while the encoder runs.  The decoder, the corner extraction and PnP then see the whole batch once.
+  int nchunk = B >= 8 ? 2 : 1;
   if (const char* ev = getenv("BOXDREAMER_B200_HOST_CHUNKS")) nchunk = atoi(ev);
   if (nchunk < 1) nchunk = 1;
-  if (nchunk > 8) nchunk = 8;
+  if (nchunk > 7) nchunk = 7;
   if (nchunk > B) nchunk = B;
   CK(cudaMemcpyAsync(e->qidx, query_idx_host, static_cast<size_t>(B) * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(e->bbox3d_q, bbox3d_q_host, static_cast<size_t>(B) * 24 * 4, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(e->K_q, K_q_host, static_cast<size_t>(B) * 9 * 4, cudaMemcpyHostToDevice, s));
   const size_t img_q = static_cast<size_t>(T) * 3 * SS * es, box_q = static_cast<size_t>(T) * 8 * SS * es;  // bytes per query
   int b0s[9];
-  for (int c = 0; c <= nchunk; ++c) b0s[c] = static_cast<int>(static_cast<long long>(B) * c / nchunk);
+  b0s[0] = 0;
+  for (int c = 1; c <= nchunk; ++c)   // chunk sizes 1 : 2 : 2 : ... (first one half as large as the others)
+    b0s[c] = c == nchunk ? B : static_cast<int>((static_cast<long long>(B) * (2 * c - 1) + (2 * nchunk - 2)) / (2 * nchunk - 1));
   for (int c = 0; c < nchunk; ++c) {
     const int b0 = b0s[c], nb = b0s[c + 1] - b0s[c];
-    CK(cudaMemcpyAsync(static_cast<char*>(e->in_images) + b0 * img_q, static_cast<const char*>(images_host) + b0 * img_q, nb * img_q,
-                       cudaMemcpyHostToDevice, e->copy_stream));
-    CK(cudaMemcpyAsync(static_cast<char*>(e->in_bbox) + b0 * box_q, static_cast<const char*>(bbox_feat_host) + b0 * box_q, nb * box_q,
-                       cudaMemcpyHostToDevice, e->copy_stream));
+    if (nb > 0)
+      CK(cudaMemcpyAsync(static_cast<char*>(e->in_images) + b0 * img_q, static_cast<const char*>(images_host) + b0 * img_q, nb * img_q,
+                         cudaMemcpyHostToDevice, e->copy_stream));
     CK(cudaEventRecord(e->copy_ev[c], e->copy_stream));
   }
+  CK(cudaMemcpyAsync(e->in_bbox, bbox_feat_host, B * box_q, cudaMemcpyHostToDevice, e->copy_stream));
+  CK(cudaEventRecord(e->copy_ev[7], e->copy_stream));
   for (int c = 0; c < nchunk; ++c) {
     const int b0 = b0s[c], nb = b0s[c + 1] - b0s[c];
-    if (nb <= 0) continue;
     CK(cudaStreamWaitEvent(s, e->copy_ev[c], 0));
-    int r = bd_forward(e, static_cast<char*>(e->in_images) + b0 * img_q, static_cast<char*>(e->in_bbox) + b0 * box_q, in_dtype,
-                       e->qidx + b0, e->bbox3d_q + b0 * 24, e->K_q + b0 * 9, e->heat + static_cast<size_t>(b0) * 8 * SS,
-                       e->corners_px + b0 * 16, e->corners_norm + b0 * 16, e->poses + b0 * 16, opts, nb, T, s);
+    if (nb <= 0) continue;
+    int r = dino_forward_impl(e, static_cast<char*>(e->in_images) + b0 * img_q, in_dtype, e->tc ? nullptr : e->feats, nb * T, s, b0 * T);
     if (r != BD_OK) return r;
+  }
+  CK(cudaStreamWaitEvent(s, e->copy_ev[7], 0));
+  {
+    int r = decoder_forward_impl(e, e->in_bbox, in_dtype, e->feats, e->tc, e->qidx, e->heat, nullptr, B, T, s);
+    if (r != BD_OK) return r;
+    LAUNCH(BD_PROF_TOPK, 1, corners_topk(e->heat, e->corners_px, e->corners_norm, nullptr, B, 8, e->S, s));
+    const PnpOpts po = to_opts(opts);
+    if (po.mode != 0 && po.mode != 1) return fail(BD_ERR_UNSUPPORTED, "bd_forward_host: pnp mode not built");
+    LAUNCH(BD_PROF_PNP, 1, pnp_solve(e->corners_px, e->bbox3d_q, e->K_q, e->poses, po, B, 8, s));
   }
   CK(cudaMemcpyAsync(corners_px_host, e->corners_px, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(corners_norm_host, e->corners_norm, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToHost, s));

@@ -8,14 +8,54 @@
 namespace bd {
 
 // ---------------------------------------------------------------------------------------------
-// top-20 over one S*S heat map per CTA.  HBM-bound: every pixel is read exactly once (coalesced),
-// each thread keeps a sorted top-20 of its strided slice in registers, then 20 block-argmax rounds merge.
+// top-20 over one S*S heat map per CTA.  HBM-bound: the map is read once from HBM (pass 1) and once more out of L2.
+//   pass 1: every thread takes the maximum of its slice (16-byte coalesced loads, no data-dependent work); the 20th
+//           largest of the 256 slice maxima is a lower bound T of the 20th largest pixel (20 distinct pixels are >= T);
+//   pass 2: pixels >= T are appended to a shared candidate list (a few dozen for real heat maps);
+//   select: each thread keeps a sorted top-20 of its share of the candidates in registers, 20 block-argmax rounds merge.
+// Degenerate maps (more than TK_CAP pixels >= T, e.g. a saturated constant map) take the exhaustive path: a sorted
+// top-20 of the thread's whole slice.  Both paths select the same set.
 // Order: larger (x+1)/2 first, ties -> lower flat index (torch.topk leaves ties unspecified).
 
 static constexpr int TOPK = 20;
 static constexpr int TK_THREADS = 256;
+static constexpr int TK_CAP = 2048;
 
 __device__ __forceinline__ bool tk_better(float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); }
+__device__ __forceinline__ float tk_value(float h) { return (h + 1.0f) * 0.5f; }  // box_utils.py:79
+
+__device__ __forceinline__ void tk_insert(float (&val)[TOPK], int (&idx)[TOPK], float v, int i) {
+  if (tk_better(v, i, val[TOPK - 1], idx[TOPK - 1])) {
+    val[TOPK - 1] = v;
+    idx[TOPK - 1] = i;
+#pragma unroll
+    for (int k = TOPK - 1; k > 0; --k) {
+      if (tk_better(val[k], idx[k], val[k - 1], idx[k - 1])) {
+        const float tv = val[k]; val[k] = val[k - 1]; val[k - 1] = tv;
+        const int ti = idx[k]; idx[k] = idx[k - 1]; idx[k - 1] = ti;
+      }
+    }
+  }
+}
+
+// block-wide argmax of (bv, bi) under tk_better; every thread receives the winner.  Two barriers.
+__device__ __forceinline__ void tk_block_best(float& bv, int& bi, float* s_val, int* s_idx) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (tk_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
+  __syncthreads();
+  bv = s_val[0]; bi = s_idx[0];
+#pragma unroll
+  for (int w = 1; w < TK_THREADS / 32; ++w) {
+    if (tk_better(s_val[w], s_idx[w], bv, bi)) { bv = s_val[w]; bi = s_idx[w]; }
+  }
+  __syncthreads();
+}
 
 __global__ void __launch_bounds__(TK_THREADS) corners_topk_kernel(const float* __restrict__ heat, float* __restrict__ corners_px,
                                                                   float* __restrict__ corners_norm, int32_t* __restrict__ idx_out,
@@ -23,45 +63,70 @@ __global__ void __launch_bounds__(TK_THREADS) corners_topk_kernel(const float* _
   const int map = blockIdx.x;
   const int n = S * S;
   const float* hm = heat + static_cast<long long>(map) * n;
+  __shared__ float s_val[TK_THREADS / 32];
+  __shared__ int s_idx[TK_THREADS / 32];
+  __shared__ float c_val[TK_CAP];
+  __shared__ int c_idx[TK_CAP];
+  __shared__ int c_cnt;
+  if (threadIdx.x == 0) c_cnt = 0;
+  const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(hm) & 15) == 0);
+  const int n4 = vec ? n / 4 : 0;
+  // ---- pass 1: slice maxima ----
+  float tmax = -INFINITY;
+  for (int i = threadIdx.x; i < n4; i += TK_THREADS) {
+    const float4 h = __ldg(reinterpret_cast<const float4*>(hm) + i);
+    tmax = fmaxf(fmaxf(tmax, fmaxf(tk_value(h.x), tk_value(h.y))), fmaxf(tk_value(h.z), tk_value(h.w)));
+  }
+  for (int i = n4 * 4 + threadIdx.x; i < n; i += TK_THREADS) tmax = fmaxf(tmax, tk_value(__ldg(hm + i)));
+  // 20th largest slice maximum (NaN-free maps; a thread without pixels holds -inf)
+  float thr = -INFINITY;
+  {
+    float mv = tmax;
+    int mi = threadIdx.x;   // "index" = owner thread: unique, so exactly one thread pops per round
+    for (int round = 0; round < TOPK; ++round) {
+      float bv = mv;
+      int bi = mi;
+      tk_block_best(bv, bi, s_val, s_idx);
+      if (mi == bi) { mv = -INFINITY; mi = INT_MAX; }
+      thr = bv;
+    }
+  }
+  // ---- pass 2: candidates >= thr ----
+  for (int i = threadIdx.x; i < n4; i += TK_THREADS) {
+    const float4 h = __ldg(reinterpret_cast<const float4*>(hm) + i);
+    const float v[4] = {tk_value(h.x), tk_value(h.y), tk_value(h.z), tk_value(h.w)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (v[k] >= thr) {
+        const int pos = atomicAdd(&c_cnt, 1);
+        if (pos < TK_CAP) { c_val[pos] = v[k]; c_idx[pos] = 4 * i + k; }
+      }
+    }
+  }
+  for (int i = n4 * 4 + threadIdx.x; i < n; i += TK_THREADS) {
+    const float v = tk_value(__ldg(hm + i));
+    if (v >= thr) {
+      const int pos = atomicAdd(&c_cnt, 1);
+      if (pos < TK_CAP) { c_val[pos] = v; c_idx[pos] = i; }
+    }
+  }
+  __syncthreads();
+  const int cnt = c_cnt;
+  // ---- select ----
   float val[TOPK];
   int idx[TOPK];
 #pragma unroll
   for (int k = 0; k < TOPK; ++k) { val[k] = -INFINITY; idx[k] = INT_MAX; }
-  for (int i = threadIdx.x; i < n; i += TK_THREADS) {
-    const float v = (__ldg(hm + i) + 1.0f) * 0.5f;  // box_utils.py:79
-    if (tk_better(v, i, val[TOPK - 1], idx[TOPK - 1])) {
-      val[TOPK - 1] = v;
-      idx[TOPK - 1] = i;
-#pragma unroll
-      for (int k = TOPK - 1; k > 0; --k) {
-        if (tk_better(val[k], idx[k], val[k - 1], idx[k - 1])) {
-          const float tv = val[k]; val[k] = val[k - 1]; val[k - 1] = tv;
-          const int ti = idx[k]; idx[k] = idx[k - 1]; idx[k - 1] = ti;
-        }
-      }
-    }
+  if (cnt <= TK_CAP && cnt >= TOPK) {
+    for (int i = threadIdx.x; i < cnt; i += TK_THREADS) tk_insert(val, idx, c_val[i], c_idx[i]);
+  } else {  // exhaustive: degenerate map (or fewer than 20 finite pixels)
+    for (int i = threadIdx.x; i < n; i += TK_THREADS) tk_insert(val, idx, tk_value(__ldg(hm + i)), i);
   }
-  __shared__ float s_val[TK_THREADS / 32];
-  __shared__ int s_idx[TK_THREADS / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int sum_x = 0, sum_y = 0;
   for (int round = 0; round < TOPK; ++round) {
     float bv = val[0];
     int bi = idx[0];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (tk_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-    }
-    if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
-    __syncthreads();
-    bv = s_val[0]; bi = s_idx[0];
-#pragma unroll
-    for (int w = 1; w < TK_THREADS / 32; ++w) {
-      if (tk_better(s_val[w], s_idx[w], bv, bi)) { bv = s_val[w]; bi = s_idx[w]; }
-    }
-    __syncthreads();
+    tk_block_best(bv, bi, s_val, s_idx);
     if (idx[0] == bi) {  // the unique owner pops its head
 #pragma unroll
       for (int k = 0; k < TOPK - 1; ++k) { val[k] = val[k + 1]; idx[k] = idx[k + 1]; }

@@ -101,6 +101,32 @@ def test_corners_topk_matches_oracle(lib):
         assert torch.equal(nm.cpu(), nm_ref)
 
 
+def test_corners_topk_ties_and_degenerate_maps(lib):
+    """The threshold pre-pass of the kernel must select the same set as an exhaustive scan: saturated maps with thousands of
+    tied maxima (the bf16 sigmoid of the reference saturates to exactly 1.0), constant maps (every pixel is a candidate:
+    exhaustive path) and a map whose maximum sits in a single slice."""
+    from oracle import boxdreamer_oracle as O
+    g = torch.Generator().manual_seed(12)
+    S = 224
+    heat = torch.empty(4, 8, S, S)
+    heat[0] = torch.tanh(4.0 * torch.randn(8, S, S, generator=g)).to(torch.bfloat16).float()   # thousands of exact +-1 ties
+    heat[1] = 1.0                                                                           # constant: lowest 20 indices win
+    heat[2] = torch.tanh(torch.randn(8, S, S, generator=g))
+    heat[2, :, 17, 16:48] = 0.9999                                                          # 32 tied maxima, contiguous
+    heat[3] = -1.0
+    heat[3, :, 200, 3] = 0.5                                                                # a single pixel above a constant floor
+    idx_ref, kp_ref, nm_ref = O.corners_topk(heat)
+    hc = heat.cuda()
+    px = torch.empty(4, 8, 2, device="cuda")
+    nm = torch.empty(4, 8, 2, device="cuda")
+    idx = torch.empty(4, 8, 20, device="cuda", dtype=torch.int32)
+    _lib.check(lib.bd_corners_topk(None, _lib.ptr(hc), _lib.ptr(px), _lib.ptr(nm), _lib.ptr(idx), 4, S, sp()))
+    torch.cuda.synchronize()
+    assert torch.equal(idx.cpu().long(), idx_ref), "top-20 indices must be bit-exact (order included)"
+    assert torch.equal(px.cpu(), kp_ref)
+    assert torch.equal(nm.cpu(), nm_ref)
+
+
 def _rot_err_deg(Ra, Rb):
     """Geodesic angle between two rotations, computed from the chordal distance so that it stays accurate for the
     float32-rounded matrices the C ABI returns (acos((tr-1)/2) loses half the digits near 0)."""

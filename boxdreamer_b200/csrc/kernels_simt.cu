@@ -327,8 +327,85 @@ __global__ void __launch_bounds__(256) patch_rows_kernel(const TIn* __restrict__
   }
 }
 
+// Fast path for 14-pixel patches with bf16 in/out (the tensor path): no run-time divisions, 16-byte global accesses.
+// One CTA per (image, patch row).  Loads: warp per image row, lane per 8-pixel chunk.  Stores: MODE 1 writes the 8
+// channels of one (token, pr, pc) as one 16-byte vector; MODE 0 writes bf16 pairs (pc, pc+1) -- a (c, pr) run of 14
+// columns starts on a 4-byte boundary only.
+template <int C, int MODE>
+__global__ void __launch_bounds__(256) patch_rows14_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int S, int kout) {
+  constexpr int P = 14;
+  extern __shared__ unsigned char smem_raw[];
+  bf16* tile = reinterpret_cast<bf16*>(smem_raw);
+  const int g = S / P;
+  const int ph = blockIdx.x;
+  const long long l = blockIdx.y;
+  const int pitch = S + 8;   // elements; rows stay 16-byte aligned, channel-strided reads spread over the banks
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = S / 8;
+  for (int row = warp; row < C * P; row += 8) {
+    const int c = row / P, pr = row % P;
+    const bf16* src = in + ((l * C + c) * S + ph * P + pr) * static_cast<long long>(S);
+    for (int ch = lane; ch < chunks; ch += 32) {
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + ch);
+      if (MODE == 0) {
+        const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+        const float stdv = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h[i]);
+          h[i] = __floats2bfloat162_rn((f.x - mean) / stdv, (f.y - mean) / stdv);
+        }
+      }
+      *reinterpret_cast<uint4*>(tile + row * pitch + ch * 8) = v;
+    }
+  }
+  __syncthreads();
+  bf16* dst = out + (l * g * g + static_cast<long long>(ph) * g) * kout;
+  if (MODE == 1) {
+    static_assert(MODE == 0 || C == 8, "patchify fast path: 8 channels = one 16-byte vector");
+    const int items = g * P * P;   // (token, pr*14 + pc)
+    for (int idx = threadIdx.x; idx < items; idx += 256) {
+      const int pw = idx / (P * P), pp = idx % (P * P);
+      const int pr = pp / P, pc = pp % P;
+      const bf16* t = tile + pr * pitch + pw * P + pc;
+      uint4 v;
+      unsigned short* hv = reinterpret_cast<unsigned short*>(&v);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) hv[c] = reinterpret_cast<const unsigned short*>(t)[c * P * pitch];
+      *reinterpret_cast<uint4*>(dst + static_cast<long long>(pw) * kout + pp * 8) = v;
+    }
+  } else {
+    const int pairs = kout / 2;
+    const int real = C * P * (P / 2);   // bf16 pairs that hold pixels; the rest is the zero pad up to kout
+    for (int idx = threadIdx.x; idx < g * pairs; idx += 256) {
+      const int pw = idx / pairs, j = idx % pairs;
+      uint32_t v = 0u;
+      if (j < real) {
+        const int c = j / (P * (P / 2)), rem = j % (P * (P / 2));
+        const int pr = rem / (P / 2), pc = (rem % (P / 2)) * 2;
+        v = *reinterpret_cast<const uint32_t*>(tile + (c * P + pr) * pitch + pw * P + pc);
+      }
+      *reinterpret_cast<uint32_t*>(dst + static_cast<long long>(pw) * kout + 2 * j) = v;
+    }
+  }
+}
+
 template <typename TIn, typename TOut, int MODE>
 static cudaError_t launch_patch_rows(const void* in, void* out, int L, int C, int S, int patch, int kout, cudaStream_t s) {
+  if constexpr (sizeof(TIn) == 2 && sizeof(TOut) == 2) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+    if (patch == 14 && S % 8 == 0 && aligned && C == (MODE == 0 ? 3 : 8) && kout % 8 == 0) {
+      const size_t smem14 = static_cast<size_t>(C) * 14 * (S + 8) * 2;
+      auto k14 = patch_rows14_kernel<(MODE == 0 ? 3 : 8), MODE>;
+      if (smem14 > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(k14, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem14));
+        if (err != cudaSuccess) return err;
+      }
+      k14<<<dim3(S / 14, L), 256, smem14, s>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), S, kout);
+      return cudaGetLastError();
+    }
+  }
   const size_t smem = static_cast<size_t>(C) * patch * (S + 2) * sizeof(TOut);
   auto kern = patch_rows_kernel<TIn, TOut, MODE>;
   if (smem > 48 * 1024) {
@@ -438,6 +515,10 @@ cudaError_t gather_query(const float* X, const int64_t* query_idx, float* out_f3
 }
 
 // unpatchify (betr.py:230-247) + sigmoid + 2x-1 (betr.py:432-435)
+__device__ __forceinline__ float heat_from_logit(float l) {
+  const float sg = 1.0f / (1.0f + expf(-l));
+  return 2.0f * sg - 1.0f;
+}
 __global__ void unpatchify_sigmoid_kernel(const float* __restrict__ logits, float* __restrict__ heat, int B, int C, int S,
                                           int patch) {
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -450,12 +531,40 @@ __global__ void unpatchify_sigmoid_kernel(const float* __restrict__ logits, floa
   const int g = S / patch;
   const int tok = (y / patch) * g + (x / patch);
   const int j = ((y % patch) * patch + (x % patch)) * C + c;
-  const float l = logits[(b * g * g + tok) * (static_cast<long long>(patch) * patch * C) + j];
-  const float sg = 1.0f / (1.0f + expf(-l));
-  heat[idx] = 2.0f * sg - 1.0f;
+  heat[idx] = heat_from_logit(logits[(b * g * g + tok) * (static_cast<long long>(patch) * patch * C) + j]);
+}
+// 8 channels: one thread per pixel reads its 8 channel logits as two 16-byte vectors (a warp covers whole 32-byte
+// sectors) and writes one float into each of the 8 channel planes (a warp writes 128 contiguous bytes per plane).
+__global__ void __launch_bounds__(256) unpatchify_sigmoid8_kernel(const float* __restrict__ logits, float* __restrict__ heat, int B, int S,
+                                                                  int patch) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long plane = static_cast<long long>(S) * S;
+  if (idx >= B * plane) return;
+  const int x = static_cast<int>(idx % S);
+  const int y = static_cast<int>((idx / S) % S);
+  const long long b = idx / plane;
+  const int g = S / patch;
+  const int tok = (y / patch) * g + (x / patch);
+  const int pp = (y % patch) * patch + (x % patch);
+  const float4* src = reinterpret_cast<const float4*>(logits + (b * g * g + tok) * (static_cast<long long>(patch) * patch * 8) + pp * 8);
+  const float4 a = __ldg(src), c4 = __ldg(src + 1);
+  float* dst = heat + b * 8 * plane + static_cast<long long>(y) * S + x;
+  dst[0 * plane] = heat_from_logit(a.x);
+  dst[1 * plane] = heat_from_logit(a.y);
+  dst[2 * plane] = heat_from_logit(a.z);
+  dst[3 * plane] = heat_from_logit(a.w);
+  dst[4 * plane] = heat_from_logit(c4.x);
+  dst[5 * plane] = heat_from_logit(c4.y);
+  dst[6 * plane] = heat_from_logit(c4.z);
+  dst[7 * plane] = heat_from_logit(c4.w);
 }
 
 cudaError_t unpatchify_sigmoid(const float* logits, float* heat, int B, int C, int S, int patch, cudaStream_t s) {
+  if (C == 8 && reinterpret_cast<uintptr_t>(logits) % 16 == 0) {
+    const long long pixels = static_cast<long long>(B) * S * S;
+    unpatchify_sigmoid8_kernel<<<static_cast<unsigned>((pixels + 255) / 256), 256, 0, s>>>(logits, heat, B, S, patch);
+    return cudaGetLastError();
+  }
   const long long total = static_cast<long long>(B) * C * S * S;
   unpatchify_sigmoid_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(logits, heat, B, C, S, patch);
   return cudaGetLastError();

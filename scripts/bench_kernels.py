@@ -66,6 +66,12 @@ if __name__ == "__main__":
             "attn_336_L34_h12_d64_N581": attention(34, 12, 64, 581, (2,)),
         }, indent=1))
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "gemm":
+        for name, r in (("proj_98304x768x768_resid", gemm(98304, 768, 768, 2)), ("fc1_98304x3072x768_gelu", gemm(98304, 3072, 768, 1)),
+                        ("fc2_98304x768x3072_resid", gemm(98304, 768, 3072, 2)), ("f32_98304x768x768", gemm(98304, 768, 768, 0)),
+                        ("act_98304x3072x3072", gemm(98304, 3072, 3072, 4)), ("dino_fc2_100224x768x3072_resid", gemm(100224, 768, 3072, 2))):
+            print(f" {name:36s} {r['ms']:8.4f} ms  {r['tflops']:7.1f} TFLOP/s")
+        sys.exit(0)
     res = {
         "attn_decoder_L64_h8_d96_N1536": attention(64, 8, 96, 1536),
         "attn_dino_L384_h12_d64_N261": attention(384, 12, 64, 261),

@@ -309,7 +309,49 @@ BD_HD void rodrigues_exp(const double (&w)[3], double (&E)[3][3]) {
 }
 
 // solve (H + lam*diag(H)) x = -g by Gaussian elimination with partial pivoting; false if singular
+// H + lam*diag(H) is symmetric positive definite whenever the LM step is well posed: unrolled Cholesky with static
+// indexing (everything stays in registers); returns false when a pivot is not positive.
+BD_HD __forceinline__ bool solve6_chol(const double (&H)[6][6], const double (&g)[6], double lam, double (&x)[6]) {
+  double L[6][6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double d = H[j][j] * (1.0 + lam);
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+    if (!(d > 0.0)) return false;
+    const double inv = 1.0 / sqrt(d);
+    L[j][j] = inv;   // reciprocal of the diagonal entry
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double v = H[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+      L[i][j] = v * inv;
+    }
+  }
+  double y[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double v = -g[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) v -= L[i][k] * y[k];
+    y[i] = v * L[i][i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double v = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) v -= L[k][i] * x[k];
+    x[i] = v * L[i][i];
+  }
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) ok = ok && isfinite(x[i]);
+  return ok;
+}
+
 BD_HD bool solve6(const double (&H)[6][6], const double (&g)[6], double lam, double (&x)[6]) {
+  if (solve6_chol(H, g, lam, x)) return true;
   double M[6][7];
   for (int i = 0; i < 6; ++i) {
     for (int j = 0; j < 6; ++j) M[i][j] = H[i][j] + (i == j ? lam * H[i][i] : 0.0);
@@ -436,11 +478,17 @@ BD_HD void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int m
         ju[3 + a] = du[a];
         jv[3 + a] = dv[a];
       }
+#pragma unroll
       for (int a = 0; a < 6; ++a) {
         g[a] += ju[a] * res[i][0] + jv[a] * res[i][1];
-        for (int b = 0; b < 6; ++b) H[a][b] += ju[a] * ju[b] + jv[a] * jv[b];
+#pragma unroll
+        for (int b = a; b < 6; ++b) H[a][b] += ju[a] * ju[b] + jv[a] * jv[b];
       }
     }
+#pragma unroll
+    for (int a = 1; a < 6; ++a)
+#pragma unroll
+      for (int b = 0; b < a; ++b) H[a][b] = H[b][a];
     bool improved = false;
     double step = 0.0, dc = 0.0;
     for (int tr = 0; tr < 12; ++tr) {

@@ -55,6 +55,7 @@ struct Att2Args {
   int heads, seq, seq_pad, BH;
   int q_off;         // first query row handled by this kernel (rows [0, q_off) are done by attention_prefix_rows)
   float scale_log2;
+  int reverse;       // walk the work items last-to-first (tc_set_reverse)
   long long* trace;  // debug: per-role clock64 stamps of CTA 0's first items (nullptr in production)
 };
 struct Att2Maps {    // Q, K: [BH*seq_pad, HD]; V^T: [BH*HD, seq_pad]; O: [L][seq][heads*HD] (3-D: rows are clipped at seq)
@@ -184,7 +185,8 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
     int st = 0;
     uint32_t ph = 0;
     int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    for (int item_f = blockIdx.x; item_f < n_items; item_f += gridDim.x, ++it) {
+      const int item = args.reverse ? n_items - 1 - item_f : item_f;
       const int bh = item / n_pairs, pair = item % n_pairs;
       const int q0 = q_off + pair * 2 * A2_BQ;
       const bool act1 = q0 + A2_BQ < seq;
@@ -231,7 +233,8 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
     // Issue order per item:  S0(0) S1(0) | for j: [S0(j+1) S1(j+1) as soon as the softmax groups hold S(j) in registers]
     // PV0(j) PV1(j).  S(j+1) is therefore already complete when a group finishes tile j: the groups never wait for the
     // tensor pipe in steady state and the kernel runs at the pace of the exp (MUFU) pipe.
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    for (int item_f = blockIdx.x; item_f < n_items; item_f += gridDim.x, ++it) {
+      const int item = args.reverse ? n_items - 1 - item_f : item_f;
       const int pair = item % n_pairs;
       const bool act1 = q_off + pair * 2 * A2_BQ + A2_BQ < seq;
       const int qb = it % QBUF;
@@ -320,7 +323,8 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
     uint32_t s_cnt = 0, d_cnt = 0;
     int pend_qb = -1, pend_arrivals = 0;    // O store in flight out of Q buffer pend_qb (storer thread only)
     int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    for (int item_f = blockIdx.x; item_f < n_items; item_f += gridDim.x, ++it) {
+      const int item = args.reverse ? n_items - 1 - item_f : item_f;
       const int bh = item / n_pairs, pair = item % n_pairs;
       const int q0 = q_off + pair * 2 * A2_BQ + g * A2_BQ;
       if (q0 >= seq) {  // inactive second tile: the whole group skips this item (but still releases its last staging tile:
@@ -563,7 +567,7 @@ static cudaError_t launch_att2(const bf16* Q, const bf16* K, const bf16* Vt, bf1
   const int n_qt = (seq - q_off + A2_BQ - 1) / A2_BQ;
   const int n_items = BH * ((n_qt + 1) / 2);
   const int grid = n_items < g_att2_sms ? n_items : g_att2_sms;
-  Att2Args a{heads, seq, seq_pad, BH, q_off, scale * 1.4426950408889634f, g_att2_trace};
+  Att2Args a{heads, seq, seq_pad, BH, q_off, scale * 1.4426950408889634f, tc_reverse(), g_att2_trace};
   kern<<<grid, A2_THREADS, Cfg::SMEM_BYTES, s>>>(tm, a);
   return cudaGetLastError();
 }

@@ -72,6 +72,7 @@ struct bd_engine {
   cudaEvent_t copy_ev[8] = {nullptr};
   // instrumentation: kernel launch counter and optional per-category CUDA-event timing
   long long launches = 0;
+  int reverse = 0;  // traversal direction of the next kernel (L2 ping-pong, tc_set_reverse)
   bool profile = false;
   struct Span { int cat; cudaEvent_t a, b; };
   std::vector<Span> spans;
@@ -366,6 +367,12 @@ static cudaError_t ln_act(bd_engine* e, const float* x, const float* w, const fl
 static int run_block(bd_engine* e, float* X, const std::string& p, int L, int seq, int seq_pad, int heads, int hd, float ln_eps,
                      bool qk_norm, const char* g1, const char* g2, int attn_cat, cudaStream_t s) {
   const int M = L * seq, d = e->d;
+  // L2 ping-pong (BD_L2_PINGPONG=1): consecutive kernels walk their rows / tiles / items in opposite directions
+  // (tc_set_reverse).  Measured on B200 at BASELINE config 2: every kernel gets 2-4 % shorter under the event profile, but
+  // the step is power-capped and the SM clock drops by the same amount -- no gain end to end, so it is off by default.
+  static const bool pingpong = getenv("BD_L2_PINGPONG") && atoi(getenv("BD_L2_PINGPONG")) != 0;
+#define BD_FLIP() do { if (pingpong) { e->reverse ^= 1; tc_set_reverse(e->reverse); } } while (0)
+  BD_FLIP();
   LAUNCH(BD_PROF_LAYERNORM, 1, ln_act(e, X, WF(e, p + "norm1.weight"), WF(e, p + "norm1.bias"), ln_eps, M, s));
   GemmEpi q;
   q.bias = WF(e, p + "attn.qkv.bias");
@@ -373,18 +380,26 @@ static int run_block(bd_engine* e, float* X, const std::string& p, int L, int se
   q.q_norm_w = qk_norm ? WF(e, p + "attn.q_norm.weight") : nullptr;
   q.k_norm_w = qk_norm ? WF(e, p + "attn.k_norm.weight") : nullptr;
   q.seq = seq; q.seq_pad = seq_pad; q.heads = heads; q.head_dim = hd; q.rms_eps = 1e-6f;
+  BD_FLIP();
   LAUNCH(BD_PROF_GEMM_QKV, e->tc ? 1 : 2, linear(e, e->H, p + "attn.qkv.weight", M, 3 * d, d, EPI_QKV, q, s));
+  BD_FLIP();
   LAUNCH(attn_cat, 1, attention(e, L, heads, hd, seq, seq_pad, s));
   GemmEpi pr;
   pr.bias = WF(e, p + "attn.proj.bias"); pr.out_f32 = X; pr.ldo = d; pr.gamma = g1 ? WF(e, p + g1) : nullptr;
+  BD_FLIP();
   LAUNCH(BD_PROF_GEMM_PROJ, 1, linear(e, e->O, p + "attn.proj.weight", M, d, d, EPI_RESID, pr, s));
+  BD_FLIP();
   LAUNCH(BD_PROF_LAYERNORM, 1, ln_act(e, X, WF(e, p + "norm2.weight"), WF(e, p + "norm2.bias"), ln_eps, M, s));
   GemmEpi f1;
   f1.bias = WF(e, p + "mlp.fc1.bias"); f1.out_act = e->G;
+  BD_FLIP();
   LAUNCH(BD_PROF_GEMM_FC1, 1, linear(e, e->H, p + "mlp.fc1.weight", M, 4 * d, d, EPI_GELU, f1, s));
   GemmEpi f2;
   f2.bias = WF(e, p + "mlp.fc2.bias"); f2.out_f32 = X; f2.ldo = d; f2.gamma = g2 ? WF(e, p + g2) : nullptr;
+  BD_FLIP();
   LAUNCH(BD_PROF_GEMM_FC2, 1, linear(e, e->G, p + "mlp.fc2.weight", M, d, 4 * d, EPI_RESID, f2, s));
+  tc_set_reverse(0);
+#undef BD_FLIP
   return BD_OK;
 }
 

@@ -52,6 +52,11 @@ cudaError_t attention_tc2(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O,
 void note_extra_launches(int n);
 int take_extra_launches();
 void tc_set_num_sms(int n);
+// Traversal direction of the next launches (tiles / rows / work items walked last-to-first when set).  The engine
+// alternates it from kernel to kernel so that each kernel starts on the data its predecessor touched last, i.e. on what
+// is still resident in the 126 MB L2 (the activations of one layer are 150-600 MB).
+void tc_set_reverse(int r);
+int tc_reverse();
 const char* tc_last_error();
 
 // --- SIMT fp32 path + memory-bound kernels (kernels_simt.cu) ---

@@ -75,7 +75,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+        const int tt = args.reverse ? num_tiles - 1 - tile : tile;
+        const int m_blk = tt / tiles_n, n_blk = tt % tiles_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
@@ -128,7 +129,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+      const int tt = args.reverse ? num_tiles - 1 - tile : tile;
+        const int m_blk = tt / tiles_n, n_blk = tt % tiles_n;
       const int row_w = m_blk * BM + quad * 32;  // first row of this warp
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -162,6 +164,9 @@ const char* tc_last_error() { return g_tc_err.c_str(); }
 static thread_local int g_extra_launches = 0;
 void note_extra_launches(int n) { g_extra_launches += n; }
 int take_extra_launches() { const int n = g_extra_launches; g_extra_launches = 0; return n; }
+static thread_local int g_reverse = 0;
+void tc_set_reverse(int r) { g_reverse = r; }
+int tc_reverse() { return g_reverse; }
 static int g_num_sms = 0;
 void tc_set_num_sms(int n) { g_num_sms = n; }
 
@@ -292,6 +297,7 @@ static cudaError_t launch(const bf16* A, const bf16* W, int M, int N, int K, con
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   GemmArgs args{M, N, K, e};
+  args.reverse = tc_reverse();
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, args);
   return cudaGetLastError();
 }

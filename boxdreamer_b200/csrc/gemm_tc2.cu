@@ -92,8 +92,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = pair; tile < num_tiles; tile += npairs) {
-      const int m_blk = args.m_fastest ? tile % tiles_m : tile / tiles_n;
-      const int n_blk = args.m_fastest ? tile / tiles_m : tile % tiles_n;
+      const int tt = args.reverse ? num_tiles - 1 - tile : tile;
+      const int m_blk = args.m_fastest ? tt % tiles_m : tt / tiles_n;
+      const int n_blk = args.m_fastest ? tt / tiles_m : tt % tiles_n;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
@@ -146,8 +147,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m_blk = args.m_fastest ? tile % tiles_m : tile / tiles_n;
-      const int n_blk = args.m_fastest ? tile / tiles_m : tile % tiles_n;
+      const int tt = args.reverse ? num_tiles - 1 - tile : tile;
+      const int m_blk = args.m_fastest ? tt % tiles_m : tt / tiles_n;
+      const int n_blk = args.m_fastest ? tt / tiles_m : tt % tiles_n;
       const int row_w = m_blk * 2 * BM + static_cast<int>(rank) * BM + quad * 32;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -225,6 +227,7 @@ static cudaError_t launch2(const bf16* A, const bf16* W, int M, int N, int K, co
   const int max_pairs = g_num_sms2 / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   GemmArgs args{M, N, K, e, col_base, m_fastest ? 1 : 0};
+  args.reverse = tc_reverse();
   kern<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, tmOut, tmOut2, args);
   return cudaGetLastError();
 }

@@ -224,9 +224,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ b, float eps, float* __restrict__ out_f32,
                                                            bf16* __restrict__ out_bf16, int rows_out, int rows_out_per,
-                                                           int rows_in_per, int row_off) {
+                                                           int rows_in_per, int row_off, int reverse) {
   constexpr int D = 768;
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int r = (reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows_out) return;
   long long rin = r;
@@ -275,7 +275,7 @@ cudaError_t layernorm(const float* x, const float* w, const float* b, float eps,
                       int d, int rows_out_per, int rows_in_per, int row_off, cudaStream_t s) {
   if (d == 768)
     layernorm768_kernel<<<(rows_out + 7) / 8, 256, 0, s>>>(x, w, b, eps, out_f32, out_bf16, rows_out, rows_out_per, rows_in_per,
-                                                           row_off);
+                                                           row_off, tc_reverse());
   else
     layernorm_kernel<<<(rows_out + 7) / 8, 256, 0, s>>>(x, w, b, eps, out_f32, out_bf16, rows_out, d, rows_out_per, rows_in_per,
                                                         row_off);

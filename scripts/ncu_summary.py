@@ -52,6 +52,9 @@ def main():
         for key, label in KEYS:
             if key in col:
                 print(f"  {label:45s} {r[col[key]]} {units[col[key]]}")
+        for h in hdr:   # whatever tensor-pipe counters this ncu version exposes for sm_100
+            if "pipe_tensor" in h and h not in dict(KEYS) and r[col[h]] not in ("", "n/a"):
+                print(f"  {h:45s} {r[col[h]]} {units[col[h]]}")
 
 
 if __name__ == "__main__":

@@ -158,7 +158,9 @@ cudaError_t corners_topk(const float* heat, float* corners_px, float* corners_no
 // A^T A by cyclic Jacobi) -> nearest rotation (Newton polar iteration) -> Levenberg-Marquardt on the pixel
 // reprojection error over all points, run to convergence, all in fp64.  One thread per query.
 
-static constexpr int PNP_MAXPTS = 16;
+static constexpr int PNP_MAXPTS = 64;   // pooled proposals of the dense multi-round path: 8 sub-batches x 8 corners
+typedef unsigned long long pmask_t;      // bit i = use point i
+static constexpr pmask_t PNP_ALL = ~0ull;
 #define BD_HD __host__ __device__
 
 // Cyclic Jacobi on a symmetric 12x12 (row-major, flat).  NOTE: written with flat indexing and non-unrolled inner
@@ -387,10 +389,10 @@ struct PnpProblem {
 // The LM / cost routines take a point mask (bit i = use point i) so hypothesis refits can share one problem.
 
 BD_HD double reproj_cost(const PnpProblem& pb, const double (&R)[3][3], const double (&t)[3], double (*res)[2],
-                              double (*Xc)[3], unsigned mask = 0xffffffffu) {
+                              double (*Xc)[3], pmask_t mask = PNP_ALL) {
   double cost = 0.0;
   for (int i = 0; i < pb.n; ++i) {
-    if (!((mask >> i) & 1u)) { if (res) { res[i][0] = 0.0; res[i][1] = 0.0; } continue; }
+    if (!((mask >> i) & 1ull)) { if (res) { res[i][0] = 0.0; res[i][1] = 0.0; } continue; }
     double xc[3];
     for (int a = 0; a < 3; ++a) xc[a] = R[a][0] * pb.X[i][0] + R[a][1] * pb.X[i][1] + R[a][2] * pb.X[i][2] + t[a];
     const double ru = pb.fx * xc[0] / xc[2] + pb.cx - pb.uv[i][0];
@@ -402,11 +404,11 @@ BD_HD double reproj_cost(const PnpProblem& pb, const double (&R)[3][3], const do
   return cost;
 }
 
-BD_HD void pnp_dlt_init(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], unsigned mask = 0xffffffffu) {
+BD_HD void pnp_dlt_init(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], pmask_t mask = PNP_ALL) {
   double A[144], V[144];
   for (int i = 0; i < 144; ++i) A[i] = 0.0;
   for (int i = 0; i < pb.n; ++i) {
-    if (!((mask >> i) & 1u)) continue;
+    if (!((mask >> i) & 1ull)) continue;
     const double xn = (pb.uv[i][0] - pb.cx) / pb.fx, yn = (pb.uv[i][1] - pb.cy) / pb.fy;
     double r1[12], r2[12];
     for (int j = 0; j < 12; ++j) { r1[j] = 0.0; r2[j] = 0.0; }
@@ -456,7 +458,7 @@ BD_HD void pnp_dlt_init(const PnpProblem& pb, double (&R)[3][3], double (&t)[3],
   nearest_rotation(R, 60);
 }
 
-BD_HD void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int max_iter, unsigned mask = 0xffffffffu) {
+BD_HD void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int max_iter, pmask_t mask = PNP_ALL) {
   double res[PNP_MAXPTS][2], Xc[PNP_MAXPTS][3];
   double lam = 1e-3;
   double cost = reproj_cost(pb, R, t, res, Xc, mask);
@@ -464,7 +466,7 @@ BD_HD void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int m
     double H[6][6], g[6];
     for (int a = 0; a < 6; ++a) { g[a] = 0.0; for (int b = 0; b < 6; ++b) H[a][b] = 0.0; }
     for (int i = 0; i < pb.n; ++i) {
-      if (!((mask >> i) & 1u)) continue;
+      if (!((mask >> i) & 1ull)) continue;
       const double x = Xc[i][0], y = Xc[i][1], z = Xc[i][2];
       const double du[3] = {pb.fx / z, 0.0, -pb.fx * x / (z * z)};
       const double dv[3] = {0.0, pb.fy / z, -pb.fy * y / (z * z)};
@@ -563,26 +565,33 @@ __global__ void __launch_bounds__(64) pnp_iterative_kernel(const float* __restri
 // 4-point subset (and, beyond those, seeded random 5-subsets) refitted from the all-point solution with a few LM steps; each is scored on ALL points (inlier count at thr_px, then truncated squared error), the warp arg-max wins and
 // is polished by LM on its inlier set.  Everything stays on the device; nothing is discarded.
 
-__device__ unsigned nth_subset_mask(int n, int k, int idx) {  // idx-th k-subset of n points in lexicographic order
-  unsigned mask = 0;
+__device__ pmask_t nth_subset_mask(int n, int k, int idx) {  // idx-th k-subset of n points in lexicographic order
+  pmask_t mask = 0;
   int x = 0;
   for (int i = 0; i < k; ++i) {
     for (;; ++x) {
       // number of subsets that start with x at position i: C(n - x - 1, k - i - 1)
-      int c = 1, nn = n - x - 1, kk = k - i - 1;
+      long long c = 1;
+      const int nn = n - x - 1, kk = k - i - 1;
       for (int j = 0; j < kk; ++j) c = c * (nn - j) / (j + 1);
       if (idx < c) break;
-      idx -= c;
+      idx -= static_cast<int>(c);
     }
-    mask |= 1u << x;
+    mask |= 1ull << x;
     ++x;
   }
   return mask;
 }
-__device__ int n_choose_k(int n, int k) {
-  int c = 1;
+__device__ int n_choose_k(int n, int k) {   // fits an int for n <= 64, k <= 6 (C(64, 6) = 74 974 368)
+  long long c = 1;
   for (int j = 0; j < k; ++j) c = c * (n - j) / (j + 1);
-  return c;
+  return static_cast<int>(c);
+}
+__device__ __forceinline__ unsigned pnp_hash(unsigned seed, unsigned q, unsigned h) {
+  unsigned x = seed ^ (q * 2654435761u) ^ (h * 40503u) ^ 0x9e3779b9u;
+  x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+  x *= 0x2c1b3c6du; x ^= x >> 15;
+  return x;
 }
 
 __global__ void __launch_bounds__(128) pnp_hypothesis_kernel(const float* __restrict__ corners, const float* __restrict__ bbox3d,
@@ -594,52 +603,63 @@ __global__ void __launch_bounds__(128) pnp_hypothesis_kernel(const float* __rest
   const int q = blockIdx.x * 4 + wq;
   if (q >= B) return;
   PnpProblem& pb = s_pb[wq];
+  for (int i = lane; i < n_pts; i += 32) {
+    for (int a = 0; a < 3; ++a) pb.X[i][a] = static_cast<double>(bbox3d[(static_cast<long long>(q) * n_pts + i) * 3 + a]);
+    for (int a = 0; a < 2; ++a) pb.uv[i][a] = static_cast<double>(corners[(static_cast<long long>(q) * n_pts + i) * 2 + a]);
+  }
   if (lane == 0) {
     pb.n = n_pts;
-    for (int i = 0; i < n_pts; ++i) {
-      for (int a = 0; a < 3; ++a) pb.X[i][a] = static_cast<double>(bbox3d[(static_cast<long long>(q) * n_pts + i) * 3 + a]);
-      for (int a = 0; a < 2; ++a) pb.uv[i][a] = static_cast<double>(corners[(static_cast<long long>(q) * n_pts + i) * 2 + a]);
-    }
     const float* Kq = Kmat + static_cast<long long>(q) * 9;
     pb.fx = Kq[0]; pb.fy = Kq[4]; pb.cx = Kq[2]; pb.cy = Kq[5];
+  }
+  __syncwarp();
+  if (lane == 0) {
     double R[3][3], t[3];
     pnp_dlt_init(pb, R, t);
     pnp_lm(pb, R, t, max_iter);
     for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) s_seed[wq][a * 3 + b] = R[a][b]; s_seed[wq][9 + a] = t[a]; }
   }
   __syncwarp();
-  const unsigned all_mask = (n_pts >= 32) ? 0xffffffffu : ((1u << n_pts) - 1u);
+  const pmask_t all_mask = (n_pts >= 64) ? PNP_ALL : ((1ull << n_pts) - 1ull);
   const double thr2 = static_cast<double>(thr_px) * thr_px;
   const int c6 = n_pts >= 6 ? n_choose_k(n_pts, 6) : 0, c5 = n_pts >= 5 ? n_choose_k(n_pts, 5) : 0, c4 = n_choose_k(n_pts, 4);
+  // Few points (the 8 corners of one proposal): the subsets are enumerated.  Pooled proposals (n_pts > 12, dense
+  // multi-round path): the subset space is sampled -- seeded random 6-point subsets, each solved from scratch.
+  const bool enumerate = static_cast<long long>(c6) + c5 + c4 <= 4096;
   // best-so-far of this lane; hypothesis "-1" is the all-point seed itself
   double bestR[3][3], bestT[3];
   int best_inl = -1;
   double best_err = 1e300;
-  unsigned best_mask = all_mask;
+  pmask_t best_mask = all_mask;
   for (int h = lane - 1; h < n_hyp; h += 32) {
     double R[3][3], t[3];
     for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) R[a][b] = s_seed[wq][a * 3 + b]; t[a] = s_seed[wq][9 + a]; }
     if (h >= 0) {
-      unsigned m;
-      if (h < c6) m = nth_subset_mask(n_pts, 6, h);
-      else if (h < c6 + c5) m = nth_subset_mask(n_pts, 5, h - c6);
-      else if (h < c6 + c5 + c4) m = nth_subset_mask(n_pts, 4, h - c6 - c5);
-      else {
-        unsigned x = seed ^ (static_cast<unsigned>(q) * 2654435761u) ^ (static_cast<unsigned>(h) * 40503u);
-        x ^= x << 13; x ^= x >> 17; x ^= x << 5;
-        m = nth_subset_mask(n_pts, 5, static_cast<int>(x % static_cast<unsigned>(c5 > 0 ? c5 : 1)));
+      pmask_t m;
+      bool from_scratch;
+      if (enumerate) {
+        if (h < c6) m = nth_subset_mask(n_pts, 6, h);
+        else if (h < c6 + c5) m = nth_subset_mask(n_pts, 5, h - c6);
+        else if (h < c6 + c5 + c4) m = nth_subset_mask(n_pts, 4, h - c6 - c5);
+        else m = nth_subset_mask(n_pts, 5, static_cast<int>(pnp_hash(seed, q, h) % static_cast<unsigned>(c5 > 0 ? c5 : 1)));
+        from_scratch = h < c6;   // 6-point subsets are solved from scratch (independent of the seed's basin)
+      } else {
+        m = nth_subset_mask(n_pts, 6, static_cast<int>(pnp_hash(seed, q, h) % static_cast<unsigned>(c6)));
+        from_scratch = true;
       }
-      if (h < c6) pnp_dlt_init(pb, R, t, m);  // 6-point subsets are solved from scratch (independent of the seed's basin)
+      if (from_scratch) pnp_dlt_init(pb, R, t, m);
       pnp_lm(pb, R, t, 6, m);
     }
-    double res[PNP_MAXPTS][2];
-    reproj_cost(pb, R, t, res, nullptr, all_mask);
     int inl = 0;
     double err = 0.0;
-    unsigned im = 0;
+    pmask_t im = 0;
     for (int i = 0; i < n_pts; ++i) {
-      const double e2 = res[i][0] * res[i][0] + res[i][1] * res[i][1];
-      if (e2 <= thr2) { ++inl; im |= 1u << i; }
+      double xc[3];
+      for (int a = 0; a < 3; ++a) xc[a] = R[a][0] * pb.X[i][0] + R[a][1] * pb.X[i][1] + R[a][2] * pb.X[i][2] + t[a];
+      const double ru = pb.fx * xc[0] / xc[2] + pb.cx - pb.uv[i][0];
+      const double rv = pb.fy * xc[1] / xc[2] + pb.cy - pb.uv[i][1];
+      const double e2 = ru * ru + rv * rv;
+      if (e2 <= thr2) { ++inl; im |= 1ull << i; }   // reprojection error only, as cv2's RANSAC callback
       err += fmin(e2, thr2);
     }
     bool ok = isfinite(err);

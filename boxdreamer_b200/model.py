@@ -372,8 +372,6 @@ class BoxDreamer(nn.Module):
             raise NotImplementedError("use_matching (LoFTR) is outside the hot path built here")
         if not (self.use_rgb and mc["encoder"]["name"] == "dino"):
             raise NotImplementedError("boxdreamer_b200 builds the DINOv2 encoder path only")
-        if self.dense_cfg is not None and bool(self.dense_cfg["enable"]):
-            raise NotImplementedError("dense_cfg.enable=True (multi-round) is a 'next' row (SURVEY.md section 8f)")
         self.rgb_encoder = DinoV2Wrapper(**mc["encoder"]["dino"])
         self.rgb_encoder._owner = self
         self.decoder = BETR(**mc["decoder"])
@@ -466,6 +464,9 @@ class BoxDreamer(nn.Module):
         camera_mask[torch.arange(B, device=dev), query_idx] = True
         data["camera_mask"] = camera_mask.clone()
 
+        if self.dense_cfg is not None and bool(self.dense_cfg["enable"]):
+            return self._forward_dense(data, camera_mask)
+
         eng = self._engine_for(images, B, T)
         imgs = self._as_engine_input(images)
         bbox_feat = data["bbox_feat"]
@@ -494,6 +495,54 @@ class BoxDreamer(nn.Module):
         data["regression_boxes"][camera_mask] = nm.to(data["regression_boxes"].dtype)
         pred_poses = poses.clone()
         if qposes is not None:
+            pred_poses[camera_mask] = qposes.to(pred_poses.dtype)
+            pred_poses = torch.nan_to_num(pred_poses, nan=0.0, posinf=0.0, neginf=0.0)
+        data["pred_poses"] = pred_poses
+        data["pred_intrinsics"] = data["intrinsics"]
+        return data
+
+    # -- dense reference sets (BoxDreamerModel.py:289-330) -------------------
+    def _pooled_pose(self, heats, bbox3d_q, K_q, n_hyp=512, thr_px=2.0):
+        """recover_pose_from_dense_bb8 (box_utils.py:202-304): top-20 corners of every proposal, all n_sub*8 2D-3D
+        pairs of a query pooled into one robust PnP (inlier threshold 2 px, as the reference's solvePnPRansac call)."""
+        B, n_sub = heats.shape[:2]
+        eng = self._engine_for(heats, B * n_sub, 1)
+        px, _ = eng.corners_topk(heats.reshape(B * n_sub, *heats.shape[2:]).float().contiguous())
+        pts2d = px.reshape(B, n_sub * 8, 2).contiguous()
+        pts3d = bbox3d_q.float().unsqueeze(1).expand(B, n_sub, 8, 3).reshape(B, n_sub * 8, 3).contiguous()
+        opts = _lib.BdPnpOpts(1, n_hyp, thr_px, 0, 30)
+        return eng.pnp(pts2d, pts3d, K_q.float().contiguous(), opts)
+
+    def _forward_dense(self, data, camera_mask):
+        from . import dense
+        cfg = self.dense_cfg
+        frames = data["images"]
+        pose_feat = data["bbox_feat"]
+        image_masks = data["image_masks"] if "image_masks" in data else torch.ones_like(frames[:, :, :1])
+        rgb_feature = self.rgb_encoder.predict(frames)     # every view is encoded once; selection works on the tokens
+        data, pose_feat, frames, camera_mask, rgb_feature, image_masks = dense.process_dense_input(
+            data, pose_feat, frames, camera_mask, rgb_feature, image_masks, cfg)
+        if bool(dense._cfg(cfg, "multi_round")):
+            heat = dense.process_multi_round(data, pose_feat, frames, camera_mask, rgb_feature, image_masks, self.decoder, cfg,
+                                             self.bbox_representation, self._pooled_pose)
+        else:
+            heat = self.decoder(pose_feat, frames, camera_mask, rgb_feature, dense.normalize(image_masks))
+        # the selection rewrote the per-view entries of `data`: everything below reads the rewritten ones
+        camera_mask = data["camera_mask"]
+        poses = data["poses"]
+        bbox_feat = data["bbox_feat"]
+        B, T = poses.shape[:2]
+        eng = self._engine_for(heat, B, T)
+        px, nm = eng.corners_topk(heat)
+        data["pred_bbox"] = bbox_feat.clone()
+        data["pred_bbox"][camera_mask] = heat.to(bbox_feat.dtype)
+        data["regression_boxes"] = data["bbox_proj_crop"].clone()
+        data["regression_boxes"][camera_mask] = nm.to(data["regression_boxes"].dtype)
+        pred_poses = poses.clone()
+        if not self.training:
+            K_q = data["non_ndc_intrinsics"][camera_mask].float().contiguous()
+            bbox3d_q = data["bbox_3d"][camera_mask].float().contiguous()
+            qposes = eng.pnp(px, bbox3d_q, K_q)
             pred_poses[camera_mask] = qposes.to(pred_poses.dtype)
             pred_poses = torch.nan_to_num(pred_poses, nan=0.0, posinf=0.0, neginf=0.0)
         data["pred_poses"] = pred_poses

@@ -90,14 +90,18 @@ int bd_corners_topk(bd_handle h, const float* heat, float* corners_px, float* co
 
 typedef struct {
   int32_t mode;      /* 0: reference parity = cv2.solvePnP(SOLVEPNP_ITERATIVE) semantics (DLT on all points -> LM)
-                        1: hypothesis mode (subset refits scored on all points, LM polish on inliers) */
+                        1: hypothesis mode = the cv2.solvePnPRansac(..., ITERATIVE) counterpart (subset solves scored on all
+                           points by reprojection error, LM refit on the winner's inliers).  n <= 12: the 6/5/4-point subsets
+                           are enumerated; pooled proposals of the dense multi-round path (utils/box_utils.py:202-304,
+                           n = 8 x sub-batches, up to 64): seeded random 6-point subsets */
   int32_t n_hyp;     /* mode 1: hypotheses per query                   */
   float thr_px;      /* mode 1: inlier threshold in pixels             */
   uint32_t seed;     /* mode 1                                         */
   int32_t max_iter;  /* LM iteration cap (0 -> 30)                     */
 } bd_pnp_opts;
 
-/* recover_pose_from_bb8 (utils/box_utils.py:113-199): corners_px [B,n,2], bbox3d [B,n,3], K [B,3,3] (fp32)
+/* recover_pose_from_bb8 (utils/box_utils.py:113-199) / recover_pose_from_dense_bb8 (:202-304):
+ * corners_px [B,n,2], bbox3d [B,n,3], K [B,3,3] (fp32), 6 <= n <= 64
  * -> poses [B,4,4] fp32 world->camera (OpenCV convention); a failed solve leaves the zero matrix. */
 int bd_pnp(bd_handle h, const float* corners_px, const float* bbox3d, const float* K, float* poses_out, const bd_pnp_opts* opts,
            int32_t B, int32_t n_pts, void* stream);

@@ -348,6 +348,26 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_value = world * B * e2e_steps / float(te.item())
 
+    # ---- the same call with the reference heat maps rasterised on the device: the caller ships the
+    # projected corners (64 B per view) instead of bbox_feat.  Reported beside `e2e`, never instead of it: the reference's
+    # input contract carries bbox_feat.
+    e2e_px = None
+    if not args.quick:
+        h_px = ((data["bbox_proj_crop"].float() + 1) / 2 * S).contiguous().pin_memory()
+        for _ in range(2):
+            eng.forward_host_px(h_images, h_px, h_qidx, h_X, h_K)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.forward_host_px(h_images, h_px, h_qidx, h_X, h_K)
+        barrier()
+        tp = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        e2e_px = {"value": world * B * e2e_steps / float(tp.item()), "unit": UNIT,
+                  "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in (h_images, h_px, h_qidx, h_K, h_X)),
+                  "d2h_bytes_per_step": d2h, "api": "bd_forward_host_px (projected corners in, heat maps rasterised on the device)"}
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
         cpu_base = cpu_baseline_sample()
@@ -366,6 +386,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "bd_forward_host (C ABI, pinned host buffers)", "steps": e2e_steps},
+            "e2e_device_rasterised_inputs": e2e_px,
             "gpu_launches": int(launches), "kernel_ms_per_step": kernel_ms, "kernel_launches_per_step": kernel_n,
             "clocks": clocks, "flops_per_query": fl["total"],
         }

@@ -66,6 +66,7 @@ struct bd_engine {
   float* corners_px = nullptr; float* corners_norm = nullptr; float* poses = nullptr;
   float* bbox3d_q = nullptr; float* K_q = nullptr; int64_t* qidx = nullptr;
   void* in_images = nullptr; void* in_bbox = nullptr;  // device staging for bd_forward_host
+  void* in_bbox_px = nullptr;                          // bd_forward_host_px: projected corners [Lmax,8,2] fp32
   float* pos_dec = nullptr;  // f32 [P, d] 2-D sincos table
   cudaStream_t host_stream = nullptr;
   cudaStream_t copy_stream = nullptr;
@@ -530,11 +531,11 @@ extern "C" int bd_forward(bd_handle e, const void* images, const void* bbox_feat
   return BD_OK;
 }
 
-extern "C" int bd_forward_host(bd_handle e, const void* images_host, const void* bbox_feat_host, int32_t in_dtype,
-                               const int64_t* query_idx_host, const float* bbox3d_q_host, const float* K_q_host,
-                               float* heat_out_host, float* corners_px_host, float* corners_norm_host, float* poses_out_host,
-                               const bd_pnp_opts* opts, int32_t B, int32_t T) {
-  if (!e || !images_host || !bbox_feat_host || !query_idx_host || !bbox3d_q_host || !K_q_host || !corners_px_host ||
+static int forward_host_impl(bd_handle e, const void* images_host, const void* bbox_feat_host, const float* bbox_px_host,
+                             int32_t in_dtype, const int64_t* query_idx_host, const float* bbox3d_q_host, const float* K_q_host,
+                             float* heat_out_host, float* corners_px_host, float* corners_norm_host, float* poses_out_host,
+                             const bd_pnp_opts* opts, int32_t B, int32_t T) {
+  if (!e || !images_host || (!bbox_feat_host && !bbox_px_host) || !query_idx_host || !bbox3d_q_host || !K_q_host || !corners_px_host ||
       !corners_norm_host || !poses_out_host)
     return fail(BD_ERR_INVALID, "bd_forward_host: null argument");
   if (B <= 0 || T <= 0 || B > e->Bmax || T > e->Tmax) return fail(BD_ERR_INVALID, "bd_forward_host: B/T exceed the workspace");
@@ -574,7 +575,14 @@ extern "C" int bd_forward_host(bd_handle e, const void* images_host, const void*
                          cudaMemcpyHostToDevice, e->copy_stream));
     CK(cudaEventRecord(e->copy_ev[c], e->copy_stream));
   }
-  CK(cudaMemcpyAsync(e->in_bbox, bbox_feat_host, B * box_q, cudaMemcpyHostToDevice, e->copy_stream));
+  if (bbox_feat_host) {
+    CK(cudaMemcpyAsync(e->in_bbox, bbox_feat_host, B * box_q, cudaMemcpyHostToDevice, e->copy_stream));
+  } else {  // 64 bytes per view instead of the maps; rasterised on the device, on the copy stream (overlaps the encoder)
+    if (!e->in_bbox_px) DALLOC(e->in_bbox_px, static_cast<size_t>(e->Lmax) * 16 * 4);
+    CK(cudaMemcpyAsync(e->in_bbox_px, bbox_px_host, static_cast<size_t>(B) * T * 16 * 4, cudaMemcpyHostToDevice, e->copy_stream));
+    CK(bbox_heatmaps(reinterpret_cast<const float*>(e->in_bbox_px), e->in_bbox, in_dtype == BD_BF16, B * T, e->S, T, e->copy_stream));
+    e->launches += 1;
+  }
   CK(cudaEventRecord(e->copy_ev[7], e->copy_stream));
   for (int c = 0; c < nchunk; ++c) {
     const int b0 = b0s[c], nb = b0s[c + 1] - b0s[c];
@@ -597,6 +605,33 @@ extern "C" int bd_forward_host(bd_handle e, const void* images_host, const void*
   CK(cudaMemcpyAsync(poses_out_host, e->poses, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToHost, s));
   if (heat_out_host) CK(cudaMemcpyAsync(heat_out_host, e->heat, static_cast<size_t>(B) * 8 * SS * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return BD_OK;
+}
+
+extern "C" int bd_forward_host(bd_handle e, const void* images_host, const void* bbox_feat_host, int32_t in_dtype,
+                               const int64_t* query_idx_host, const float* bbox3d_q_host, const float* K_q_host,
+                               float* heat_out_host, float* corners_px_host, float* corners_norm_host, float* poses_out_host,
+                               const bd_pnp_opts* opts, int32_t B, int32_t T) {
+  if (!bbox_feat_host) return fail(BD_ERR_INVALID, "bd_forward_host: null argument");
+  return forward_host_impl(e, images_host, bbox_feat_host, nullptr, in_dtype, query_idx_host, bbox3d_q_host, K_q_host, heat_out_host,
+                           corners_px_host, corners_norm_host, poses_out_host, opts, B, T);
+}
+
+extern "C" int bd_forward_host_px(bd_handle e, const void* images_host, const float* bbox_px_host, int32_t in_dtype,
+                                  const int64_t* query_idx_host, const float* bbox3d_q_host, const float* K_q_host,
+                                  float* heat_out_host, float* corners_px_host, float* corners_norm_host,
+                                  float* poses_out_host, const bd_pnp_opts* opts, int32_t B, int32_t T) {
+  if (!bbox_px_host) return fail(BD_ERR_INVALID, "bd_forward_host_px: null argument");
+  return forward_host_impl(e, images_host, nullptr, bbox_px_host, in_dtype, query_idx_host, bbox3d_q_host, K_q_host, heat_out_host,
+                           corners_px_host, corners_norm_host, poses_out_host, opts, B, T);
+}
+
+extern "C" int bd_make_bbox_features(const float* bbox_px, void* out, int32_t out_dtype, int32_t L, int32_t S, int32_t group,
+                                     void* stream) {
+  if (!bbox_px || !out || L <= 0 || S <= 0 || group <= 0 || L % group != 0) return fail(BD_ERR_INVALID, "bd_make_bbox_features: bad argument");
+  if (out_dtype != BD_F32 && out_dtype != BD_BF16) return fail(BD_ERR_INVALID, "bd_make_bbox_features: dtype must be BD_F32 or BD_BF16");
+  cudaError_t err = bbox_heatmaps(bbox_px, out, out_dtype == BD_BF16, L, S, group, reinterpret_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) return fail(BD_ERR_CUDA, std::string("bd_make_bbox_features: ") + cudaGetErrorString(err));
   return BD_OK;
 }
 

@@ -570,6 +570,71 @@ cudaError_t unpatchify_sigmoid(const float* logits, float* heat, int B, int C, i
   return cudaGetLastError();
 }
 
+// make_bbox_features(type="heatmap") of the dataset (src/datasets/utils/base/bbox_utils.py:263-303) on the device: one
+// CTA per (view, corner).  heat = 2 * exp(-d / s) / max - 1 with d the pixel's distance to the projected corner,
+// s = (|corner - centre of the 8 corners| / 10)^2 and `max` the maximum of corner i's un-normalised maps over the `group`
+// views rasterised by one reference call (`bbox_map[..., i].max()`, :296; the dataset calls it per sample, group = T).
+// exp is monotone and the pixel nearest to the corner minimises |dx| and |dy| separately, so a view's maximum is
+// exp(-d(nearest pixel) / s): O(1) per view, no reduction pass.  Every operation is a separate IEEE fp32 operation in the
+// reference's order (no FMA contraction); only expf may differ from the host's by an ulp.
+__device__ __forceinline__ float heat_dist(float bx, float by, int x, int y) {
+  const float dx = __fsub_rn(bx, static_cast<float>(x)), dy = __fsub_rn(by, static_cast<float>(y));
+  return sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+}
+__device__ __forceinline__ float heat_scale(const float* c, int i) {   // c: the 8 corners of one view
+  float sx = 0.f, sy = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sx = __fadd_rn(sx, c[2 * k]); sy = __fadd_rn(sy, c[2 * k + 1]); }
+  const float cx = __fdiv_rn(sx, 8.0f), cy = __fdiv_rn(sy, 8.0f);
+  const float ex = __fsub_rn(cx, c[2 * i]), ey = __fsub_rn(cy, c[2 * i + 1]);
+  const float q = __fdiv_rn(sqrtf(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey))), 10.0f);
+  return __fmul_rn(q, q);
+}
+__device__ __forceinline__ int heat_nearest(float b, int S) {
+  const float r = fminf(fmaxf(nearbyintf(b), 0.0f), static_cast<float>(S - 1));
+  return static_cast<int>(r);
+}
+template <typename TOut>
+__global__ void __launch_bounds__(256) bbox_heatmap_kernel(const float* __restrict__ corners, TOut* __restrict__ out, int S, int group) {
+  const int i = blockIdx.x;
+  const long long l = blockIdx.y;
+  const long long g0 = (l / group) * group;
+  float vmax = 0.0f;
+  for (int v = 0; v < group; ++v) {
+    const float* cv = corners + (g0 + v) * 16;
+    const float bxv = cv[2 * i], byv = cv[2 * i + 1];
+    const float dmin = heat_dist(bxv, byv, heat_nearest(bxv, S), heat_nearest(byv, S));
+    vmax = fmaxf(vmax, expf(__fdiv_rn(-dmin, heat_scale(cv, i))));
+  }
+  const float* c = corners + l * 16;
+  const float bx = c[2 * i], by = c[2 * i + 1];
+  // per pixel: distance, one multiply, ex2, one FMA.  The fast forms (rsqrt-based distance, __expf, reciprocals hoisted out
+  // of the loop) stay within 1e-6 of the reference's IEEE sequence on values in [-1, 1] (the stated tolerance is 4e-6);
+  // the normaliser vmax above uses the exact sequence.
+  const float neg_inv_s = __fdiv_rn(-1.0f, heat_scale(c, i));
+  const float k = __fdiv_rn(2.0f, vmax);
+  const int n = S * S;
+  TOut* dst = out + (l * 8 + i) * n;
+  int x = threadIdx.x % S, y = threadIdx.x / S;
+  const int step_y = 256 / S, step_x = 256 % S;
+  for (int p = threadIdx.x; p < n; p += 256) {
+    const float dx = bx - static_cast<float>(x), dy = by - static_cast<float>(y);
+    const float d2 = fmaf(dx, dx, dy * dy);
+    const float d = d2 > 0.0f ? d2 * rsqrtf(d2) : 0.0f;
+    dst[p] = static_cast<TOut>(fmaf(__expf(d * neg_inv_s), k, -1.0f));
+    x += step_x; y += step_y;
+    if (x >= S) { x -= S; ++y; }
+  }
+}
+
+cudaError_t bbox_heatmaps(const float* corners_px, void* out, int out_is_bf16, int L, int S, int group, cudaStream_t s) {
+  if (L <= 0) return cudaSuccess;
+  if (group <= 0 || L % group != 0) return cudaErrorInvalidValue;
+  if (out_is_bf16) bbox_heatmap_kernel<bf16><<<dim3(8, L), 256, 0, s>>>(corners_px, reinterpret_cast<bf16*>(out), S, group);
+  else bbox_heatmap_kernel<float><<<dim3(8, L), 256, 0, s>>>(corners_px, reinterpret_cast<float*>(out), S, group);
+  return cudaGetLastError();
+}
+
 __global__ void cast_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (idx < n) out[idx] = __float2bfloat16_rn(in[idx]);

@@ -177,6 +177,20 @@ class Engine:
         return heat, px, nm, poses
 
 
+    def forward_host_px(self, images, bbox_px, query_idx, bbox3d_q, K_q, want_heat=False, opts=None):
+        """forward_host with the reference heat maps rasterised on the device from bbox_px [B,T,8,2] (host, fp32)."""
+        B, T = images.shape[:2]
+        heat = torch.empty(B, 8, self.S, self.S, dtype=torch.float32).pin_memory() if want_heat else None
+        px = torch.empty(B, 8, 2, dtype=torch.float32).pin_memory()
+        nm = torch.empty(B, 8, 2, dtype=torch.float32).pin_memory()
+        poses = torch.empty(B, 4, 4, dtype=torch.float32).pin_memory()
+        o = C.byref(opts) if opts is not None else None
+        _lib.check(self.lib.bd_forward_host_px(self.handle, _lib.ptr(images), _lib.ptr(bbox_px), self._dt(images),
+                                               _lib.ptr(query_idx), _lib.ptr(bbox3d_q), _lib.ptr(K_q), _lib.ptr(heat),
+                                               _lib.ptr(px), _lib.ptr(nm), _lib.ptr(poses), o, B, T), "bd_forward_host_px")
+        return heat, px, nm, poses
+
+
 # ----------------------------------------------------------------------------------------------
 # parameter containers with the reference's state_dict layout
 
@@ -464,6 +478,16 @@ class BoxDreamer(nn.Module):
         camera_mask[torch.arange(B, device=dev), query_idx] = True
         data["camera_mask"] = camera_mask.clone()
 
+        if "bbox_feat" not in data:
+            # device-side input synthesis: the dataset ships the projected corners in crop
+            # pixels ("bbox_proj_px" [B,T,8,2], fp32) instead of the 8*S*S heat maps (src/datasets/base.py:689-693)
+            if "bbox_proj_px" not in data:
+                raise KeyError("data needs 'bbox_feat' (reference contract) or 'bbox_proj_px' (device-side synthesis)")
+            from .inputs import make_bbox_features
+            feat_dtype = images.dtype if images.dtype in (torch.float32, torch.bfloat16) else torch.float32
+            data["bbox_feat"] = make_bbox_features(data["bbox_proj_px"].to(dev).reshape(B * T, 8, 2), "heatmap",
+                                                   (self.image_size, self.image_size), dtype=feat_dtype, group=T).view(
+                B, T, 8, self.image_size, self.image_size)
         if self.dense_cfg is not None and bool(self.dense_cfg["enable"]):
             return self._forward_dense(data, camera_mask)
 

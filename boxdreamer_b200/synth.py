@@ -159,10 +159,15 @@ def project(K: np.ndarray, R: np.ndarray, t: np.ndarray, X: np.ndarray) -> np.nd
     return uv[:, :2] / uv[:, 2:3]
 
 
-def make_heatmaps(corners_px: torch.Tensor, S: int) -> torch.Tensor:
+def make_heatmaps(corners_px: torch.Tensor, S: int, group: int = 1) -> torch.Tensor:
     """GT 8-corner heatmaps in [-1,1]; follows datasets/utils/base/bbox_utils.py:263-303.
 
     corners_px [L,8,2] (pixel coords of the crop) -> [L,8,S,S] fp32.
+    `group`: number of consecutive views normalised together.  The reference divides corner i's maps by their maximum
+    over the WHOLE call (`bbox_map[..., i].max()`, bbox_utils.py:296), and the dataset calls it once per sample, i.e.
+    over that sample's T views: group=T is the dataset's semantics (what `bd_make_bbox_features` implements and what
+    tests/test_oracle_vs_reference.py pins).  group=1 (per-view maximum, the default) is what the synthetic inputs of
+    the committed golden fixtures were generated with; the two differ by ~1e-3 in the map values.
     """
     L = corners_px.shape[0]
     c = corners_px.to(torch.float32)
@@ -175,7 +180,12 @@ def make_heatmaps(corners_px: torch.Tensor, S: int) -> torch.Tensor:
     dis = torch.sqrt((center[:, None, 0] - c[:, :, 0]) ** 2 + (center[:, None, 1] - c[:, :, 1]) ** 2)
     scale = (dis / 10) ** 2
     m = torch.exp(-dist / scale.view(L, 8, 1, 1))
-    m = m / m.amax(dim=(2, 3), keepdim=True)
+    if group == 1:
+        m = m / m.amax(dim=(2, 3), keepdim=True)
+    else:
+        assert L % group == 0
+        mg = m.view(L // group, group, 8, S, S)
+        m = (mg / mg.amax(dim=(1, 3, 4), keepdim=True)).view(L, 8, S, S)
     return m * 2 - 1
 
 

@@ -122,6 +122,22 @@ int bd_forward_host(bd_handle h, const void* images_host, const void* bbox_feat_
                     float* corners_px_host, float* corners_norm_host, float* poses_out_host, const bd_pnp_opts* opts,
                     int32_t B, int32_t T);
 
+/* ---- input synthesis on the device ---- */
+
+/* make_bbox_features(bbox, type="heatmap", shape=(S,S)) of the dataset (src/datasets/utils/base/bbox_utils.py:263-303):
+ * bbox_px [L,8,2] fp32 projected box corners in crop pixels (make_proj_bbox, camera_utils.py:62-84)
+ * -> out [L,8,S,S] in out_dtype (BD_F32 | BD_BF16; the dataset casts to its `precision`, src/datasets/base.py:715-765).
+ * `group`: consecutive views rasterised by ONE reference call -- corner i's maps are divided by their maximum over the call
+ * (bbox_utils.py:296); the dataset calls per sample, so group = T (must divide L). */
+int bd_make_bbox_features(const float* bbox_px, void* out, int32_t out_dtype, int32_t L, int32_t S, int32_t group, void* stream);
+
+/* bd_forward_host with the reference heat maps rasterised on the device: the caller ships 64 bytes per view
+ * (bbox_px_host [B,T,8,2] fp32) instead of 8*S*S elements; everything else as bd_forward_host. */
+int bd_forward_host_px(bd_handle h, const void* images_host, const float* bbox_px_host, int32_t in_dtype,
+                       const int64_t* query_idx_host, const float* bbox3d_q_host, const float* K_q_host, float* heat_out_host,
+                       float* corners_px_host, float* corners_norm_host, float* poses_out_host, const bd_pnp_opts* opts,
+                       int32_t B, int32_t T);
+
 /* ---- kernel-level entry points (used by the unit tests and bench.py's roofline leg) ---- */
 
 /* out = epilogue(A[M,K] . W[N,K]^T + bias).  precision selects the kernel (bf16: A,W bf16; exact: fp32).

@@ -194,3 +194,27 @@ def test_336px_long_sequence_config(weights):
         if precision == "exact":
             px, nm, idx = eng.corners_topk(heat, want_idx=True)
             assert torch.equal(torch.sort(idx.cpu().long(), dim=2).values, torch.sort(ref["topk_idx"], dim=2).values)
+
+
+def test_forward_from_projected_corners_equals_forward_from_heatmaps(weights):
+    """Device-side input synthesis: a batch that carries 'bbox_proj_px' instead of 'bbox_feat' must give the same result
+    (exact precision; the rasterised maps differ from the CPU-made ones by <= 4e-6, tests/test_gpu_simt.py)."""
+    B, T = 2, 3
+    data = synth.synth_inputs(B, T, 224, seed=79)
+    px = (data["bbox_proj_crop"].float() + 1) / 2 * 224
+    data["bbox_feat"] = synth.make_heatmaps(px.view(B * T, 8, 2), 224, group=T).view(B, T, 8, 224, 224)   # dataset semantics
+    m = _model(weights, "exact")
+    ref = m(_to_cuda(data))
+    alt = {k: v for k, v in _to_cuda(data).items() if k != "bbox_feat"}
+    alt["bbox_proj_px"] = px
+    out = m(alt)
+    assert _scaled(out["pred_bbox"], ref["pred_bbox"]) <= 1e-4
+    assert torch.allclose(out["regression_boxes"], ref["regression_boxes"], atol=0.2 / 224 * 2)   # top-20 means: <= 0.2 px
+    # host-buffer entry with corners (64 B per view) == host-buffer entry with maps
+    eng = m._engine_for(ref["pred_bbox"], B, T)
+    mask = ref["camera_mask"].cpu()
+    args = (data["query_idx"], data["bbox_3d"][mask].float().contiguous(), data["non_ndc_intrinsics"][mask].float().contiguous())
+    h1, px1, _, p1 = eng.forward_host(data["images"].contiguous(), data["bbox_feat"].contiguous(), *args, want_heat=True)
+    h2, px2, _, p2 = eng.forward_host_px(data["images"].contiguous(), alt["bbox_proj_px"].contiguous(), *args, want_heat=True)
+    assert float((h1 - h2).abs().max()) <= 1e-4 * float(h1.abs().max())
+    assert float((px1 - px2).abs().max()) <= 0.2

@@ -193,3 +193,26 @@ def test_pnp_hypothesis_mode_rejects_outlier_corners(lib):
     C0, C1 = solve(c2, None), solve(c2, opts)
     d = np.array([_rot_err_deg(C0[i, :3, :3], C1[i, :3, :3]) for i in range(n)])
     assert np.median(d) < 0.2  # clean corners: the hypothesis mode may drop a noisy corner but stays at the same solution
+
+
+def test_bbox_heatmap_rasteriser_matches_restatement(lib):
+    """bd_make_bbox_features (device) vs synth.make_heatmaps, the torch restatement pinned bit-exact to the dataset's
+    make_bbox_features on CPU (tests/test_oracle_vs_reference.py).  Every operation but exp is a correctly rounded fp32
+    operation in the reference's order; expf may differ by an ulp or two from the host's, hence 4e-6 absolute on values in
+    [-1, 1]; after the dataset's bf16 cast at most one bf16 ulp on <= 0.1 % of the pixels.  Includes corners outside the crop."""
+    from boxdreamer_b200 import synth
+    from boxdreamer_b200.inputs import make_bbox_features
+    for S in (224, 336):
+        data = synth.synth_inputs(3, 4, S, seed=5)
+        px = ((data["bbox_proj_crop"].float() + 1) / 2 * S).view(12, 8, 2)
+        px[0, 0] = torch.tensor([-13.25, 7.5])            # outside the crop: the maximum sits on the border
+        px[1, 3] = torch.tensor([S + 40.0, S - 0.5])
+        ref = synth.make_heatmaps(px, S, group=4)         # the dataset rasterises one sample (T = 4 views) per call
+        got = make_bbox_features(px.cuda(), "heatmap", (S, S), group=4)
+        assert got.shape == (12, 8, S, S)
+        assert float((got.cpu() - ref).abs().max()) <= 4e-6
+        got16 = make_bbox_features(px.cuda(), "heatmap", (S, S), dtype=torch.bfloat16, group=4).cpu()
+        assert float((make_bbox_features(px.cuda(), "heatmap", (S, S)).cpu() - synth.make_heatmaps(px, S, group=12)).abs().max()) <= 4e-6
+        ref16 = ref.to(torch.bfloat16)
+        diff = (got16.float() - ref16.float()).abs()
+        assert float((diff > 0).float().mean()) <= 1e-3 and float(diff.max()) <= 2 ** -7

@@ -32,3 +32,23 @@ def test_reference_state_dict_layout():
     assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == {k: tuple(v) for k, v in synth.decoder_param_shapes().items()}
     dsd = model.rgb_encoder.model.state_dict()
     assert {k: tuple(v.shape) for k, v in dsd.items()} == {k: tuple(v) for k, v in synth.dino_param_shapes().items()}
+
+
+def test_input_synthesis_restatement_equals_reference():
+    """synth.make_heatmaps / inputs.make_proj_bbox (the CPU side of the device rasteriser's parity test) against the
+    dataset's own make_bbox_features(type='heatmap') and make_proj_bbox (bbox_utils.py:263-303, camera_utils.py:62-84)."""
+    ref_import.install()
+    from src.datasets.utils.base.bbox_utils import make_bbox_features as ref_feat
+    from src.datasets.utils.base.camera_utils import make_proj_bbox as ref_proj
+    from boxdreamer_b200.inputs import make_proj_bbox
+    data = synth.synth_inputs(2, 3, 224, seed=99)
+    poses = data["poses"].view(6, 4, 4)
+    K = data["non_ndc_intrinsics"].view(6, 3, 3)
+    X = data["bbox_3d"].view(6, 8, 3)
+    proj_ref = ref_proj(poses, K, X)
+    proj = make_proj_bbox(poses, K, X)
+    assert torch.allclose(proj, proj_ref, atol=1e-3, rtol=1e-6)      # pixels; fp32 matmul association differs
+    heat_ref = ref_feat(proj_ref, "heatmap", (224, 224))
+    heat = synth.make_heatmaps(proj_ref, 224, group=6)      # one reference call = one normalisation group
+    assert heat.shape == heat_ref.shape == (6, 8, 224, 224)
+    assert torch.equal(heat, heat_ref)

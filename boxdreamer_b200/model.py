@@ -525,6 +525,45 @@ class BoxDreamer(nn.Module):
         data["pred_intrinsics"] = data["intrinsics"]
         return data
 
+    # -- reference-feature cache ------------------------------------------------
+    @torch.no_grad()
+    def encode_references(self, images, bbox_feat):
+        """Encodes a reference set once: images [R,3,S,S], bbox_feat [R,8,S,S] (the views every query of a video / demo
+        session shares; the reference re-encodes them for every query, BoxDreamerModel.py:274-285).  Returns the cache to
+        pass to `forward_with_references`."""
+        R = images.shape[0]
+        eng = self._engine_for(images, R, 1)
+        feats = eng.dino_forward(self._as_engine_input(images))
+        return {"feats": feats, "bbox_feat": bbox_feat, "n_ref": R}
+
+    @torch.no_grad()
+    def forward_with_references(self, query_images, cache, bbox3d_q, K_q):
+        """query_images [B,3,S,S] against the cached reference set: only the B query crops go through the encoder
+        (1/(R+1) of the encoder work), then the usual decoder over [R references + query] per sample, top-20 corners and
+        PnP.  Returns the query-view entries of the reference's output dict:
+        pred_bbox [B,8,S,S], regression_boxes [B,8,2] (normalised), keypoints [B,8,2] (pixels), pred_poses [B,4,4].
+        Identical to `forward` on a batch whose every sample lists the cached references followed by the query."""
+        B = query_images.shape[0]
+        R = cache["n_ref"]
+        T = R + 1
+        dev = query_images.device
+        eng = self._engine_for(query_images, B, T)
+        q_feats = eng.dino_forward(self._as_engine_input(query_images))                     # [B,P,d]
+        feats = torch.cat([cache["feats"].unsqueeze(0).expand(B, R, *q_feats.shape[1:]), q_feats.unsqueeze(1)], dim=1).contiguous()
+        ref_maps = cache["bbox_feat"]
+        bbox = torch.cat([ref_maps.unsqueeze(0).expand(B, R, *ref_maps.shape[1:]),
+                          torch.zeros(B, 1, *ref_maps.shape[1:], device=dev, dtype=ref_maps.dtype)], dim=1).contiguous()
+        bbox = self._as_engine_input(bbox)
+        if bbox.dtype != self._as_engine_input(query_images).dtype:
+            bbox = bbox.to(self._as_engine_input(query_images).dtype)
+        query_idx = torch.full((B,), R, dtype=torch.int64, device=dev)
+        heat = eng.decoder_forward(bbox, feats, query_idx)       # the query's own map is replaced by the learnable token
+        px, nm = eng.corners_topk(heat)
+        out = {"pred_bbox": heat, "regression_boxes": nm, "keypoints": px}
+        if not self.training:
+            out["pred_poses"] = torch.nan_to_num(eng.pnp(px, bbox3d_q.float().contiguous(), K_q.float().contiguous()), nan=0.0, posinf=0.0, neginf=0.0)
+        return out
+
     # -- dense reference sets (BoxDreamerModel.py:289-330, SURVEY.md section 8f rank 1) -------------------
     def _pooled_pose(self, heats, bbox3d_q, K_q, n_hyp=512, thr_px=2.0):
         """recover_pose_from_dense_bb8 (box_utils.py:202-304): top-20 corners of every proposal, all n_sub*8 2D-3D

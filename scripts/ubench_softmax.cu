@@ -76,6 +76,23 @@ __global__ void __launch_bounds__(256, 1) k(int iters, float c, long long* cyc, 
     if (MODE == 1) {
 #pragma unroll
       for (int i = 0; i < BKV / 2; ++i) sv[i] = pack_bf16x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1]));
+    } else if (MODE == 4 || MODE == 5) {
+      // packed-fp32 scale and row sum (FFMA2 / FADD2): half the FMA-pipe instructions of the scalar loop.  MODE 5: no row sum.
+      const f32x2 c2 = pack_f32x2(c, c), n2 = pack_f32x2(nmc, nmc);
+      f32x2 acc0 = pack_f32x2(0.f, 0.f), acc1 = pack_f32x2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < BKV / 2; i += 2) {
+        float x0, x1, x2, x3;
+        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2, n2), x0, x1);
+        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * i + 2]), __uint_as_float(sv[2 * i + 3])), c2, n2), x2, x3);
+        const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
+        if (MODE == 4) { acc0 = add_f32x2(acc0, pack_f32x2(p0, p1)); acc1 = add_f32x2(acc1, pack_f32x2(p2, p3)); }
+        sv[i] = pack_bf16x2(p0, p1);
+        sv[i + 1] = pack_bf16x2(p2, p3);
+      }
+      float a, b, d, e;
+      unpack_f32x2(acc0, a, b); unpack_f32x2(acc1, d, e);
+      ps0 = a; ps1 = b; ps2 = d; ps3 = e;
     } else {
       uint32_t pk[BKV / 2];
 #pragma unroll
@@ -144,7 +161,10 @@ int main() {
     run<3, 96, 1>("1 of 4 exps on the FMA pipe", nw);
     run<3, 96, 2>("2 of 4 exps on the FMA pipe", nw);
     run<3, 96, 4>("all exps on the FMA pipe", nw);
+    run<4, 96>("packed FFMA2/FADD2 scale + row sum", nw);
+    run<5, 96>("packed scale, no row sum (sum on the tensor core)", nw);
     run<0, 128>("kernel loop (ld, max, exp, pack, st)", nw);
+    run<4, 128>("packed FFMA2/FADD2 scale + row sum", nw);
     run<2, 128>("exp phase only", nw);
     run<3, 128, 1>("1 of 4 exps on the FMA pipe", nw);
     run<3, 128, 2>("2 of 4 exps on the FMA pipe", nw);

@@ -218,3 +218,28 @@ def test_forward_from_projected_corners_equals_forward_from_heatmaps(weights):
     h2, px2, _, p2 = eng.forward_host_px(data["images"].contiguous(), alt["bbox_proj_px"].contiguous(), *args, want_heat=True)
     assert float((h1 - h2).abs().max()) <= 1e-4 * float(h1.abs().max())
     assert float((px1 - px2).abs().max()) <= 0.2
+
+
+def test_reference_feature_cache_equals_full_forward(weights):
+    """Rank-2 widening: queries that share a reference set re-use its encoder tokens.  Same kernels, exact precision ->
+    the cached path must reproduce the full forward bit for bit."""
+    B, R = 3, 2
+    base = synth.synth_inputs(1, R + 1, 224, seed=80)                     # one sample: R references + a query slot
+    other = synth.synth_inputs(B, R + 1, 224, seed=81)                    # B different query crops / intrinsics
+    full = {}
+    for k, v in other.items():
+        if torch.is_tensor(v) and v.dim() >= 2 and v.shape[1] == R + 1:
+            w = v.clone()
+            w[:, :R] = base[k][0, :R]                                      # every sample lists the same references
+            full[k] = w
+        else:
+            full[k] = v
+    full["query_idx"] = torch.full((B,), R, dtype=torch.int64)
+    m = _model(weights, "exact")
+    ref = m(_to_cuda(full))
+    cache = m.encode_references(base["images"][0, :R].cuda(), base["bbox_feat"][0, :R].cuda())
+    out = m.forward_with_references(full["images"][:, R].cuda(), cache, full["bbox_3d"][:, R].cuda(), full["non_ndc_intrinsics"][:, R].cuda())
+    mask = ref["camera_mask"]
+    assert torch.equal(out["pred_bbox"], ref["pred_bbox"][mask])
+    assert torch.equal(out["regression_boxes"], ref["regression_boxes"][mask])
+    assert torch.equal(out["pred_poses"], ref["pred_poses"][mask])

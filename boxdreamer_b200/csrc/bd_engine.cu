@@ -626,6 +626,14 @@ extern "C" int bd_forward_host_px(bd_handle e, const void* images_host, const fl
                            corners_px_host, corners_norm_host, poses_out_host, opts, B, T);
 }
 
+extern "C" int bd_pose_metrics(const float* pose_pred, const float* pose_gt, const float* K, const float* model_pts,
+                               int64_t pts_stride, float* out, int32_t B, int32_t N, void* stream) {
+  if (!pose_pred || !pose_gt || !K || !model_pts || !out || B <= 0 || N <= 0) return fail(BD_ERR_INVALID, "bd_pose_metrics: bad argument");
+  cudaError_t err = pose_metrics(pose_pred, pose_gt, K, model_pts, pts_stride, out, B, N, reinterpret_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) return fail(BD_ERR_CUDA, std::string("bd_pose_metrics: ") + cudaGetErrorString(err));
+  return BD_OK;
+}
+
 extern "C" int bd_make_bbox_features(const float* bbox_px, void* out, int32_t out_dtype, int32_t L, int32_t S, int32_t group,
                                      void* stream) {
   if (!bbox_px || !out || L <= 0 || S <= 0 || group <= 0 || L % group != 0) return fail(BD_ERR_INVALID, "bd_make_bbox_features: bad argument");

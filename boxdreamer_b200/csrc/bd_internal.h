@@ -85,6 +85,8 @@ cudaError_t gather_query(const float* X, const int64_t* query_idx, float* out_f3
 // logits [B*P, patch*patch*C] -> heat [B,C,S,S] = 2*sigmoid(l) - 1 (betr.py:230-247, 432-435); optional raw logits image
 cudaError_t unpatchify_sigmoid(const float* logits, float* heat, int B, int C, int S, int patch, cudaStream_t s);
 cudaError_t cast_f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t s);
+cudaError_t pose_metrics(const float* pose_pred, const float* pose_gt, const float* K, const float* pts, long long pts_stride,
+                         float* out, int B, int N, cudaStream_t s);
 cudaError_t bbox_heatmaps(const float* corners_px, void* out, int out_is_bf16, int L, int S, int group, cudaStream_t s);
 // SIMT-path QKV post-processing: qkv [M, 3*d] fp32 -> Q,K (RMSNorm optional), V [BH, seq_pad, hd] fp32
 cudaError_t qkv_split_f32(const float* qkv, const GemmEpi& e, int M, cudaStream_t s);

@@ -694,6 +694,133 @@ __global__ void __launch_bounds__(128) pnp_hypothesis_kernel(const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pose metrics of the evaluation step (src/lightning/utils/metrics/metric_utils.py): rotation / translation / in-plane
+// error (:162-210), mean 2-D projection error of the model points (:224-306), ADD and ADD-S (:331-424) -- one CTA per
+// query, the model points stay on the device (the reference moves the batch to the CPU and walks it with a thread pool
+// and a cKDTree per query).  ADD-S is a brute-force nearest neighbour over shared-memory tiles of the predicted points.
+// out[q] = {rot_deg, trans_norm, inplane_deg, proj2d_mean, add_mean, adds_mean, diameter, 0}.
+
+static constexpr int PM_THREADS = 256;
+static constexpr int PM_TILE = 1024;
+
+__device__ __forceinline__ float pm_block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < PM_THREADS / 32; ++w) s += red[w];
+  return s;
+}
+
+__global__ void __launch_bounds__(PM_THREADS) pose_metrics_kernel(const float* __restrict__ pose_pred, const float* __restrict__ pose_gt,
+                                                                  const float* __restrict__ Kmat, const float* __restrict__ pts,
+                                                                  long long pts_stride, float* __restrict__ out, int N) {
+  __shared__ float sp[12], sg[12], sk[9], red[PM_THREADS / 32];
+  __shared__ float tile[PM_TILE][3];
+  __shared__ float bmin[3][PM_THREADS / 32], bmax[3][PM_THREADS / 32];
+  const int q = blockIdx.x;
+  if (threadIdx.x < 12) { sp[threadIdx.x] = pose_pred[q * 12 + threadIdx.x]; sg[threadIdx.x] = pose_gt[q * 12 + threadIdx.x]; }
+  if (threadIdx.x < 9) sk[threadIdx.x] = Kmat[q * 9 + threadIdx.x];
+  __syncthreads();
+  const float* P = pts + static_cast<long long>(q) * pts_stride;
+  float proj = 0.f, add = 0.f, adds = 0.f;
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  // ADD-S needs, for every ground-truth-posed point, its nearest predicted-posed point: tiles of predicted points in smem
+  const int n_round = (N + PM_THREADS - 1) / PM_THREADS;
+  for (int r = 0; r < n_round; ++r) {
+    const int i = r * PM_THREADS + threadIdx.x;
+    const bool live = i < N;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (live) { x = P[3 * i]; y = P[3 * i + 1]; z = P[3 * i + 2]; }
+    float pp[3], pg[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      pp[a] = sp[a * 4] * x + sp[a * 4 + 1] * y + sp[a * 4 + 2] * z + sp[a * 4 + 3];
+      pg[a] = sg[a * 4] * x + sg[a * 4 + 1] * y + sg[a * 4 + 2] * z + sg[a * 4 + 3];
+    }
+    float best = INFINITY;
+    for (int t0 = 0; t0 < N; t0 += PM_TILE) {
+      __syncthreads();
+      for (int j = threadIdx.x; j < PM_TILE && t0 + j < N; j += PM_THREADS) {
+        const float u = P[3 * (t0 + j)], v = P[3 * (t0 + j) + 1], w = P[3 * (t0 + j) + 2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) tile[j][a] = sp[a * 4] * u + sp[a * 4 + 1] * v + sp[a * 4 + 2] * w + sp[a * 4 + 3];
+      }
+      __syncthreads();
+      const int nt = min(PM_TILE, N - t0);
+      if (live) {
+        for (int j = 0; j < nt; ++j) {
+          const float dx = tile[j][0] - pg[0], dy = tile[j][1] - pg[1], dz = tile[j][2] - pg[2];
+          best = fminf(best, dx * dx + dy * dy + dz * dz);
+        }
+      }
+    }
+    if (live) {
+      adds += sqrtf(best);
+      const float dx = pp[0] - pg[0], dy = pp[1] - pg[1], dz = pp[2] - pg[2];
+      add += sqrtf(dx * dx + dy * dy + dz * dz);
+      float up[3], ug[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        up[a] = sk[a * 3] * pp[0] + sk[a * 3 + 1] * pp[1] + sk[a * 3 + 2] * pp[2];
+        ug[a] = sk[a * 3] * pg[0] + sk[a * 3 + 1] * pg[1] + sk[a * 3 + 2] * pg[2];
+      }
+      const float ex = up[0] / up[2] - ug[0] / ug[2], ey = up[1] / up[2] - ug[1] / ug[2];
+      proj += sqrtf(ex * ex + ey * ey);
+      mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+      mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+    }
+  }
+  const float s_proj = pm_block_sum(proj, red), s_add = pm_block_sum(add, red), s_adds = pm_block_sum(adds, red);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float lo = mn[a], hi = mx[a];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((threadIdx.x & 31) == 0) { bmin[a][threadIdx.x >> 5] = lo; bmax[a][threadIdx.x >> 5] = hi; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float d2 = 0.f;
+    for (int a = 0; a < 3; ++a) {
+      float lo = bmin[a][0], hi = bmax[a][0];
+      for (int w = 1; w < PM_THREADS / 32; ++w) { lo = fminf(lo, bmin[a][w]); hi = fmaxf(hi, bmax[a][w]); }
+      d2 += (hi - lo) * (hi - lo);
+    }
+    // rotation_diff = R_pred R_gt^T; angle from its trace, in-plane angle from its first column (metric_utils.py:186-208)
+    float rd[3][3];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) rd[a][b] = sp[a * 4] * sg[b * 4] + sp[a * 4 + 1] * sg[b * 4 + 1] + sp[a * 4 + 2] * sg[b * 4 + 2];
+    const float tr = fminf(fmaxf(rd[0][0] + rd[1][1] + rd[2][2], -1.0f), 3.0f);
+    float ang = acosf(fminf(fmaxf((tr - 1.0f) * 0.5f, -1.0f), 1.0f)) * 57.29577951308232f;
+    const float tx = sp[3] - sg[3], ty = sp[7] - sg[7], tz = sp[11] - sg[11];
+    float te = sqrtf(tx * tx + ty * ty + tz * tz);
+    if (!isfinite(ang)) ang = 0.f;
+    if (!isfinite(te)) te = 0.f;
+    float* o = out + q * 8;
+    o[0] = ang;
+    o[1] = te;
+    o[2] = fabsf(atan2f(rd[1][0], rd[0][0]) * 57.29577951308232f);
+    o[3] = s_proj / N;
+    o[4] = s_add / N;
+    o[5] = s_adds / N;
+    o[6] = sqrtf(d2);
+    o[7] = 0.f;
+  }
+}
+
+cudaError_t pose_metrics(const float* pose_pred, const float* pose_gt, const float* K, const float* pts, long long pts_stride,
+                         float* out, int B, int N, cudaStream_t s) {
+  if (B <= 0) return cudaSuccess;
+  if (N <= 0) return cudaErrorInvalidValue;
+  pose_metrics_kernel<<<B, PM_THREADS, 0, s>>>(pose_pred, pose_gt, K, pts, pts_stride, out, N);
+  return cudaGetLastError();
+}
+
 cudaError_t pnp_solve(const float* corners_px, const float* bbox3d, const float* K, float* poses, const PnpOpts& o, int B,
                       int n_pts, cudaStream_t s) {
   if (B <= 0) return cudaSuccess;

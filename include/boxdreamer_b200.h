@@ -138,6 +138,17 @@ int bd_forward_host_px(bd_handle h, const void* images_host, const float* bbox_p
                        float* corners_px_host, float* corners_norm_host, float* poses_out_host, const bd_pnp_opts* opts,
                        int32_t B, int32_t T);
 
+/* ---- evaluation metrics on the device ---- */
+
+/* Per-query pose metrics of src/lightning/utils/metrics/metric_utils.py: query_pose_error (:162-210),
+ * process_single_bs_2d (:255-306), process_single_bs_add (:331-424).  pose_pred / pose_gt [B,3,4] fp32 (the prediction
+ * already scaled and moved to the ground truth's frame, :280-281), K [B,3,3], model_pts [N,3] fp32 shared by all queries
+ * (pts_stride = 0) or one cloud per query (pts_stride = 3*N).
+ * -> out [B,8] = {rotation error (deg), |t_pred - t_gt| (pose units), in-plane rotation error (deg), mean 2-D projection
+ *    error (px), ADD mean distance, ADD-S mean nearest-neighbour distance, model diameter (bounding-box diagonal), 0}. */
+int bd_pose_metrics(const float* pose_pred, const float* pose_gt, const float* K, const float* model_pts, int64_t pts_stride,
+                    float* out, int32_t B, int32_t N, void* stream);
+
 /* ---- kernel-level entry points (used by the unit tests and bench.py's roofline leg) ---- */
 
 /* out = epilogue(A[M,K] . W[N,K]^T + bias).  precision selects the kernel (bf16: A,W bf16; exact: fp32).

@@ -552,10 +552,12 @@ static int forward_host_impl(bd_handle e, const void* images_host, const void* b
     CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&e->copy_ev[i], cudaEventDisableTiming));
   }
-  // Copy order = consumption order: the encoder only needs the images, so they go first, in `nchunk` pieces of whole queries
-  // (the first one small: its transfer is the only one nothing can hide); the reference heat maps (73 % of the bytes)
-  // follow and land while the encoder runs.  The decoder, the corner extraction and PnP then see the whole batch once.
-  int nchunk = B >= 8 ? 2 : 1;
+  // Copy order = consumption order: the encoder only needs the images, so they go first; the reference heat maps (73 % of
+  // the bytes) follow and land while the encoder runs.  The decoder, the corner extraction and PnP then see the whole batch
+  // once.  The images can be split into `nchunk` pieces of whole queries (first one half-sized) so that the encoder starts
+  // earlier, but at BASELINE config 2 the smaller encoder GEMMs cost more than the 2 ms of exposed transfer they hide
+  // (scripts/bench_e2e_chunks.py on B200: 1 chunk 49.3 ms, 2: 50.7, 3: 51.8, 4: 51.1) -- default 1.
+  int nchunk = 1;
   if (const char* ev = getenv("BOXDREAMER_B200_HOST_CHUNKS")) nchunk = atoi(ev);
   if (nchunk < 1) nchunk = 1;
   if (nchunk > 7) nchunk = 7;

@@ -206,62 +206,102 @@ BD_HD void jacobi_eig_sym12(double* A, double* V) {
   }
 }
 
-// Eigenvector of the smallest eigenvalue of a symmetric positive semi-definite 12x12 (row-major, flat) by inverse
-// iteration on the Cholesky factor of (A + eps*tr*I): ~25x less work than the full Jacobi decomposition and the
-// serial latency that dominates one-thread-per-query PnP.  Returns false when the factorisation breaks down (the
-// caller then falls back to Jacobi).  L overwrites the lower triangle of A.
-BD_HD bool smallest_eigvec_sym12(double* A, double* x) {
+// Eigenvector of the smallest eigenvalue of a symmetric positive semi-definite 12x12 (row-major, flat; only the upper
+// triangle and the diagonal are read).  Inverse iteration on a Cholesky factor with a Rayleigh-quotient shift: three
+// plain steps on A + eps*tr*I find the neighbourhood, then every step re-factors A - mu*I with mu = rho - 1.5*|A x - rho x|,
+// which lies below the eigenvalue nearest to rho (so the factorisation exists once x has settled on the smallest one) and
+// converges super-linearly -- a handful of steps where the fixed shift needs up to 60 when noise makes the two smallest
+// eigenvalues comparable (that tail dominated the latency of one-thread-per-query PnP).  Returns false when a
+// factorisation breaks down or the iteration does not settle (the caller then falls back to Jacobi).
+BD_HD bool chol12_shifted(const double* A, double mu, double* L) {   // L L^T = A - mu*I ; L: lower triangle, row-major
+  for (int j = 0; j < 12; ++j) {
+    double d = A[j * 13] - mu;
+#pragma unroll 1
+    for (int k = 0; k < j; ++k) d -= L[j * 12 + k] * L[j * 12 + k];
+    if (!(d > 1e-300)) return false;
+    d = sqrt(d);
+    L[j * 13] = d;
+#pragma unroll 1
+    for (int i = j + 1; i < 12; ++i) {
+      double v = A[j * 12 + i];   // upper triangle of the symmetric input
+#pragma unroll 1
+      for (int k = 0; k < j; ++k) v -= L[i * 12 + k] * L[j * 12 + k];
+      L[i * 12 + j] = v / d;
+    }
+  }
+  return true;
+}
+BD_HD bool chol12_step(const double* L, double* x) {   // x <- normalised (L L^T)^-1 x, sign kept; returns false on breakdown
+  double y[12];
+#pragma unroll 1
+  for (int i = 0; i < 12; ++i) {
+    double v = x[i];
+#pragma unroll 1
+    for (int k = 0; k < i; ++k) v -= L[i * 12 + k] * y[k];
+    y[i] = v / L[i * 13];
+  }
+#pragma unroll 1
+  for (int i = 11; i >= 0; --i) {
+    double v = y[i];
+#pragma unroll 1
+    for (int k = i + 1; k < 12; ++k) v -= L[k * 12 + i] * y[k];
+    y[i] = v / L[i * 13];
+  }
+  double n = 0.0, dot = 0.0;
+  for (int i = 0; i < 12; ++i) { n += y[i] * y[i]; dot += x[i] * y[i]; }
+  n = sqrt(n);
+  if (!(n > 0.0) || !isfinite(n)) return false;
+  const double sc = (dot < 0.0 ? -1.0 : 1.0) / n;
+  for (int i = 0; i < 12; ++i) x[i] = y[i] * sc;
+  return true;
+}
+BD_HD bool smallest_eigvec_sym12(const double* A, double* x) {
   double tr = 0.0;
   for (int i = 0; i < 12; ++i) tr += A[i * 13];
   if (!(tr > 0.0)) return false;
-  const double shift = 1e-10 * tr;
-  for (int j = 0; j < 12; ++j) {
-    double d = A[j * 13] + shift;
-#pragma unroll 1
-    for (int k = 0; k < j; ++k) d -= A[j * 12 + k] * A[j * 12 + k];
-    if (!(d > 1e-300)) return false;
-    d = sqrt(d);
-    A[j * 13] = d;
-#pragma unroll 1
-    for (int i = j + 1; i < 12; ++i) {
-      double v = A[i * 12 + j];
-#pragma unroll 1
-      for (int k = 0; k < j; ++k) v -= A[i * 12 + k] * A[j * 12 + k];
-      A[i * 12 + j] = v / d;
-    }
+  double L[144];
+  if (!chol12_shifted(A, -1e-10 * tr, L)) return false;
+  {
+    double n0 = 0.0;
+    for (int i = 0; i < 12; ++i) { x[i] = 1.0 / (1.0 + i); n0 += x[i] * x[i]; }
+    n0 = 1.0 / sqrt(n0);
+    for (int i = 0; i < 12; ++i) x[i] *= n0;
   }
-  for (int i = 0; i < 12; ++i) x[i] = 1.0 / (1.0 + i);
-  double y[12];
-  for (int it = 0; it < 60; ++it) {
+  for (int it = 0; it < 3; ++it)
+    if (!chol12_step(L, x)) return false;
+  double mu_prev = -1e-10 * tr;
+  for (int it = 0; it < 40; ++it) {
+    // Rayleigh quotient and residual with the symmetric product (upper triangle)
+    double y[12], rho = 0.0;
 #pragma unroll 1
     for (int i = 0; i < 12; ++i) {
-      double v = x[i];
+      double v = 0.0;
 #pragma unroll 1
-      for (int k = 0; k < i; ++k) v -= A[i * 12 + k] * y[k];
-      y[i] = v / A[i * 13];
+      for (int k = 0; k < 12; ++k) v += (k >= i ? A[i * 12 + k] : A[k * 12 + i]) * x[k];
+      y[i] = v;
+      rho += v * x[i];
     }
-#pragma unroll 1
-    for (int i = 11; i >= 0; --i) {
-      double v = y[i];
-#pragma unroll 1
-      for (int k = i + 1; k < 12; ++k) v -= A[k * 12 + i] * y[k];
-      y[i] = v / A[i * 13];
+    double r2 = 0.0;
+    for (int i = 0; i < 12; ++i) r2 += (y[i] - rho * x[i]) * (y[i] - rho * x[i]);
+    const double r = sqrt(r2);
+    if (r <= 1e-15 * tr) return true;                       // residual at the fp64 resolution of the matrix
+    double mu = rho - 1.5 * r;
+    bool ok = chol12_shifted(A, mu, L);
+    if (!ok) {                                               // x still carries a larger eigenvalue: retreat towards the last good shift
+      mu = 0.5 * (mu + mu_prev);
+      ok = chol12_shifted(A, mu, L);
+      if (!ok) { mu = mu_prev; ok = chol12_shifted(A, mu, L); }
+      if (!ok) return false;
     }
-    double n = 0.0;
-    for (int i = 0; i < 12; ++i) n += y[i] * y[i];
-    n = sqrt(n);
-    if (!(n > 0.0) || !isfinite(n)) return false;
-    double diff = 0.0, dot = 0.0;
-    for (int i = 0; i < 12; ++i) dot += x[i] * y[i];
-    const double sgn = dot < 0.0 ? -1.0 : 1.0;
-    for (int i = 0; i < 12; ++i) {
-      const double xn = sgn * y[i] / n;
-      diff += (xn - x[i]) * (xn - x[i]);
-      x[i] = xn;
-    }
-    if (diff < 1e-26 && it >= 2) break;
+    mu_prev = mu < mu_prev ? mu_prev : mu;
+    double xo[12];
+    for (int i = 0; i < 12; ++i) xo[i] = x[i];
+    if (!chol12_step(L, x)) return false;
+    double diff = 0.0;
+    for (int i = 0; i < 12; ++i) diff += (x[i] - xo[i]) * (x[i] - xo[i]);
+    if (diff < 1e-28) return true;
   }
-  return true;
+  return false;
 }
 
 BD_HD __forceinline__ double det3(const double (&R)[3][3]) {
@@ -422,9 +462,8 @@ BD_HD void pnp_dlt_init(const PnpProblem& pb, double (&R)[3][3], double (&t)[3],
   }
   double Rd[3][3], td[3];
   {
-    double B[144], ev[12];
-    for (int i = 0; i < 144; ++i) B[i] = A[i];
-    if (smallest_eigvec_sym12(B, ev)) {
+    double ev[12];
+    if (smallest_eigvec_sym12(A, ev)) {
       for (int a = 0; a < 3; ++a) {
         for (int b = 0; b < 3; ++b) Rd[a][b] = ev[a * 4 + b];
         td[a] = ev[a * 4 + 3];

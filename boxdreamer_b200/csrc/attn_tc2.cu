@@ -349,9 +349,9 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
       for (int j = 0; j < n_kv; ++j) {
         const int kv0 = j * BKV;
         const bool last = (j == n_kv - 1);
-        if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 4 + 0);
+        if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 8 + 0);
         mbar_wait(&s_full[g], s_cnt & 1);
-        if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 4 + 1);
+        if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 8 + 1);
         ++s_cnt;
         tc_fence_after();
         float alpha = 1.0f;
@@ -366,7 +366,7 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_free[g]);
           }
-          if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 4 + 2);
+          if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 8 + 2);
           float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
           for (int i = 0; i < BKV; i += 8) {
@@ -386,6 +386,7 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
           float nmc = -m_run * c;
           float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
           if (turns) a2_turn_wait(g, nmc, turn_slot);
+          if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 8 + 4);
           // The turn is handed over when A2_PASS_NUM/A2_PASS_DEN of the exponentials are done: the other group's first
           // exponentials overlap this group's last ones, which hides the hand-over latency without starving the MUFU pipe.
           constexpr int PASS_I = ((BKV / 2) * A2_PASS_NUM / A2_PASS_DEN) & ~1;
@@ -402,6 +403,8 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
             sv[i + 1] = pack_bf16x2(p2, p3);
           }
           l_run += (ps0 + ps1) + (ps2 + ps3);
+          if (quad == 0 && lane == 0 && args.trace != nullptr && blockIdx.x == 0 && (it * n_kv + j) * 8 + 5 < 512)
+            args.trace[(1 + g) * 512 + (it * n_kv + j) * 8 + 5] = clock64() + (__float_as_uint(l_run) & 0);   // after the exp loop (data-dependent)
           if (j > 0) {  // PV_g(j-1) must have finished reading P_g and writing O_g
             mbar_wait(&pv_done[g], d_cnt & 1);
             ++d_cnt;
@@ -471,7 +474,7 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g]);
-        if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 4 + 3);
+        if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 8 + 3);
         // the previous item's O store has long finished reading its staging tile: release that Q buffer to the producer
         if (storer && pend_qb >= 0) {
           bulk_wait_group_read<0>();

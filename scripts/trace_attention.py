@@ -21,15 +21,17 @@ run()
 torch.cuda.synchronize()
 lib.bd_debug_attention_trace(None)
 ev = tr.cpu()[3 * 512:].view(64, 8)
-t = tr.cpu()[:3 * 512].view(3, 128, 4)
-t0 = int(t[t > 0].min())
+t = tr.cpu()[:512].view(128, 4)
+sm = tr.cpu()[512:3 * 512].view(2, 64, 8)
+allv = tr.cpu()[:3 * 512]
+t0 = int(allv[allv > 0].min())
 bkv = 96 if hd == 96 else 128
 n_kv = (seq + bkv - 1) // bkv
-print("item j | MMA: waitP0 start/end, waitP1 start/end | SM0: wait start, S seen, ld done, arrive | SM1: ...   (cycles since first stamp)")
-for idx in range(2 * n_kv + 4):
-    row = [int(x) - t0 if int(x) > 0 else -1 for x in t[:, idx, :].reshape(-1)]
-    print(f"{idx // n_kv:2d} {idx % n_kv:2d} | " + " ".join(f"{v:7d}" for v in row[0:4]) + " | " + " ".join(f"{v:7d}" for v in row[4:8]) + " | " +
-          " ".join(f"{v:7d}" for v in row[8:12]))
+print("item j | MMA: waitP0 start/end, waitP1 start/end | SM0: wait start, S seen, ld done, arrive, turn granted, exp done | SM1: ...   (cycles since first stamp)")
+rel = lambda x: int(x) - t0 if int(x) > 0 else -1
+for idx in range(min(2 * n_kv + 4, 64)):
+    print(f"{idx // n_kv:2d} {idx % n_kv:2d} | " + " ".join(f"{rel(v):7d}" for v in t[idx]) + " | " + " ".join(f"{rel(v):7d}" for v in sm[0, idx, :6]) + " | " +
+          " ".join(f"{rel(v):7d}" for v in sm[1, idx, :6]))
 print("item | producer: q_empty wait start / done | MMA: item start, q_full seen, k_full seen | softmax g0: last pv_done seen")
 for i in range(4):
     print(f"{i:2d} | " + " ".join(f"{int(x) - t0 if int(x) > 0 else -1:7d}" for x in ev[i, :6]))

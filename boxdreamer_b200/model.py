@@ -350,7 +350,7 @@ class DinoV2Wrapper:
         if self._owner is None:
             raise RuntimeError("DinoV2Wrapper must be owned by a boxdreamer_b200.BoxDreamer")
         L = input_tensor.shape[0]
-        eng = self._owner._engine_for(input_tensor, L, 1)
+        eng = self._owner._engine_for(input_tensor, 1, 1, images=L)
         ret = eng.dino_forward(self._owner._as_engine_input(input_tensor))
         if flag:
             ret = ret.view(B, T, *ret.shape[1:])
@@ -420,19 +420,25 @@ class BoxDreamer(nn.Module):
             t = t.float()
         return t.contiguous()
 
-    def _engine_for(self, like: torch.Tensor, B: int, T: int) -> Engine:
+    def _engine_for(self, like: torch.Tensor, B: int, T: int, images: int = 0) -> Engine:
+        """The engine (workspace) for B sequences of T views; `images` additionally asks for room for that many images in
+        the encoder (its calls are not tied to the B x T shape).  The workspace scales with max_batch * max_views images,
+        so when it has to grow it keeps that product at what is needed instead of multiplying the old maxima: the dense path
+        mixes (B*T images, 1 view), (B*n_sub, sub+1) and (B, fine_topk+1) calls and would otherwise allocate ~6x too much."""
         if not like.is_cuda:
             raise _lib.BoxDreamerLibError("boxdreamer_b200: inputs must be CUDA tensors (no CPU fallback); "
                                           "call model.cuda() and move the batch to the GPU")
         prec = self._pick_precision(like)
         key = (prec, like.device.index)
         eng = self._engines.get(key)
+        need = max(B * T, images)
         with torch.cuda.device(like.device):
-            if eng is None or eng.max_batch * eng.max_views < B * T or eng.max_batch < B or eng.max_views < T:
+            if eng is None or eng.max_batch * eng.max_views < need or eng.max_batch < B or eng.max_views < T:
+                old_images = eng.max_batch * eng.max_views if eng is not None else 0
+                mv = max(T, eng.max_views if eng else 0)
+                mb = max(B, -(-max(need, old_images) // mv))
                 if eng is not None:
                     eng.close()
-                mb = max(B, eng.max_batch if eng else 0)
-                mv = max(T, eng.max_views if eng else 0)
                 eng = Engine(self.image_size, self.patch_size, self.decoder.d_model, self.decoder.att_depth,
                              self.decoder.nhead, prec, mb, mv)
                 self._engines[key] = eng
@@ -532,7 +538,7 @@ class BoxDreamer(nn.Module):
         session shares; the reference re-encodes them for every query, BoxDreamerModel.py:274-285).  Returns the cache to
         pass to `forward_with_references`."""
         R = images.shape[0]
-        eng = self._engine_for(images, R, 1)
+        eng = self._engine_for(images, 1, 1, images=R)
         feats = eng.dino_forward(self._as_engine_input(images))
         return {"feats": feats, "bbox_feat": bbox_feat, "n_ref": R}
 
@@ -569,7 +575,7 @@ class BoxDreamer(nn.Module):
         """recover_pose_from_dense_bb8 (box_utils.py:202-304): top-20 corners of every proposal, all n_sub*8 2D-3D
         pairs of a query pooled into one robust PnP (inlier threshold 2 px, as the reference's solvePnPRansac call)."""
         B, n_sub = heats.shape[:2]
-        eng = self._engine_for(heats, B * n_sub, 1)
+        eng = self._engine_for(heats, 1, 1)    # top-20 and PnP need no workspace
         px, _ = eng.corners_topk(heats.reshape(B * n_sub, *heats.shape[2:]).float().contiguous())
         pts2d = px.reshape(B, n_sub * 8, 2).contiguous()
         pts3d = bbox3d_q.float().unsqueeze(1).expand(B, n_sub, 8, 3).reshape(B, n_sub * 8, 3).contiguous()

@@ -386,7 +386,9 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
           float nmc = -m_run * c;
           float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
           if (turns) a2_turn_wait(g, nmc, turn_slot);
+#ifdef A2_TRACE_FINE   // two more stamps inside the exp phase (scripts/build_variant.sh fine attn_tc2.cu -DA2_TRACE_FINE): they cost ~2 %
           if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 8 + 4);
+#endif
           // The turn is handed over when A2_PASS_NUM/A2_PASS_DEN of the exponentials are done: the other group's first
           // exponentials overlap this group's last ones, which hides the hand-over latency without starving the MUFU pipe.
           constexpr int PASS_I = ((BKV / 2) * A2_PASS_NUM / A2_PASS_DEN) & ~1;
@@ -403,8 +405,10 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
             sv[i + 1] = pack_bf16x2(p2, p3);
           }
           l_run += (ps0 + ps1) + (ps2 + ps3);
+#ifdef A2_TRACE_FINE
           if (quad == 0 && lane == 0 && args.trace != nullptr && blockIdx.x == 0 && (it * n_kv + j) * 8 + 5 < 512)
             args.trace[(1 + g) * 512 + (it * n_kv + j) * 8 + 5] = clock64() + (__float_as_uint(l_run) & 0);   // after the exp loop (data-dependent)
+#endif
           if (j > 0) {  // PV_g(j-1) must have finished reading P_g and writing O_g
             mbar_wait(&pv_done[g], d_cnt & 1);
             ++d_cnt;

@@ -58,8 +58,11 @@ def load_model(model, path: str | None, dino_path: str | None = None, device=Non
         if missing:
             raise KeyError(f"checkpoint {path} lacks {len(missing)} decoder tensors, e.g. {missing[:3]}")
         if dino_path is not None:
-            dino = torch.load(dino_path, map_location="cpu") if not dino_path.endswith(".safetensors") else \
-                __import__("safetensors.torch", fromlist=["load_file"]).load_file(dino_path, device="cpu")
+            if dino_path.endswith(".safetensors"):
+                from safetensors.torch import load_file
+                dino = load_file(dino_path, device="cpu")
+            else:
+                dino = torch.load(dino_path, map_location="cpu")
     if world > 1:
         dec = bdist.broadcast_state(dec, dec_shapes, src=0, device=device, group=group)
         flag = torch.tensor([1 if (rank == 0 and dino is not None) else 0], device=device)

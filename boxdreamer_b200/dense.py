@@ -183,6 +183,10 @@ def process_multi_round(data, pose_feat, frames, camera_mask, rgb_feature, image
     Also stores the coarse result in data["dense_coarse_poses"] (not a reference key)."""
     if bbox_representation != "heatmap":
         raise NotImplementedError("multi-round: heatmap representation only")
+    if not _cfg(dense_cfg, "fine_level"):
+        raise NotImplementedError(
+            "dense_cfg.multi_round without fine_level returns the data dict where BoxDreamer.forward expects a heat map "
+            "(dense_processing.py:145-158 vs BoxDreamerModel.py:343-344): that configuration fails in the reference too")
     B = frames.shape[0]
     poses = data["poses"]
     K_q = data["non_ndc_intrinsics"][camera_mask]
@@ -199,10 +203,6 @@ def process_multi_round(data, pose_feat, frames, camera_mask, rgb_feature, image
         heats = heats.reshape(B, n_sub, *heats.shape[1:])
     query_poses = pooled_pose_fn(heats, bbox3d_q, K_q)
     data["dense_coarse_poses"] = query_poses
-    if not _cfg(dense_cfg, "fine_level"):
-        raise NotImplementedError(
-            "dense_cfg.multi_round without fine_level returns the data dict where BoxDreamer.forward expects a heat map "
-            "(dense_processing.py:145-158 vs BoxDreamerModel.py:343-344): that configuration fails in the reference too")
     ref_poses, _ = _split_query(poses, camera_mask)
     idx = fetch_neighbors_by_pose_similarity(ref_poses.float(), query_poses.float(), topk=_cfg(dense_cfg, "fine_topk"))
     neighbor_mask = _mask_from_indices(idx, ref_poses.shape[1])

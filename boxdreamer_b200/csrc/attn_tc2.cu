@@ -174,9 +174,11 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
     tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // (BD_PDL builds) everything above overlapped the predecessor's tail; no global access before this point
   // broadcast through a shuffle so the compiler keeps the TMEM base (and everything derived from it) in uniform registers
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
@@ -578,8 +580,12 @@ static cudaError_t launch_att2(const bf16* Q, const bf16* K, const bf16* Vt, bf1
   const int n_items = BH * ((n_qt + 1) / 2);
   const int grid = n_items < g_att2_sms ? n_items : g_att2_sms;
   Att2Args a{heads, seq, seq_pad, BH, q_off, scale * 1.4426950408889634f, tc_reverse(), g_att2_trace};
+#ifdef BD_PDL
+  return launch_pdl(kern, dim3(grid), dim3(A2_THREADS), Cfg::SMEM_BYTES, s, tm, a);
+#else
   kern<<<grid, A2_THREADS, Cfg::SMEM_BYTES, s>>>(tm, a);
   return cudaGetLastError();
+#endif
 }
 
 // Rows [0, nrows) (nrows <= 8) of every sequence: one WARP per (image, head), flash-style over 96-key chunks with
@@ -611,6 +617,8 @@ __global__ void __launch_bounds__(PFX_WARPS * 32) attention_prefix_rows_kernel(c
   constexpr int OT = HD / 8;           // 8-dim output tiles
   const int lane = threadIdx.x & 31;
   const int bh = blockIdx.x * PFX_WARPS + (threadIdx.x >> 5);
+  pdl_launch_dependents();
+  pdl_wait();
   if (bh >= BH) return;
   const int g = lane >> 2, q = lane & 3;
   const bf16* Qb = Q + static_cast<long long>(bh) * seq_pad * HD;
@@ -704,8 +712,13 @@ static cudaError_t launch_prefix(const bf16* Q, const bf16* K, const bf16* Vt, b
   const float sl = scale * 1.4426950408889634f;
   const int BH = L * heads;
   note_extra_launches(1);
+#ifdef BD_PDL
+  return launch_pdl(attention_prefix_rows_kernel<HD>, dim3((BH + PFX_WARPS - 1) / PFX_WARPS), dim3(PFX_WARPS * 32), 0, s, Q, K, Vt, O, BH, heads, seq,
+                    seq_pad, nrows, sl);
+#else
   attention_prefix_rows_kernel<HD><<<(BH + PFX_WARPS - 1) / PFX_WARPS, PFX_WARPS * 32, 0, s>>>(Q, K, Vt, O, BH, heads, seq, seq_pad, nrows, sl);
   return cudaGetLastError();
+#endif
 }
 
 cudaError_t attention_tc2(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int head_dim, int seq,

@@ -82,9 +82,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS);
     tmem_relinquish_2sm();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   cluster_sync_all();   // barriers of BOTH CTAs are initialised before anyone signals across the pair
   tc_fence_after();
+  pdl_wait();           // (BD_PDL builds) no global access before this point
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
   if (warp == 0) {
@@ -228,8 +230,12 @@ static cudaError_t launch2(const bf16* A, const bf16* W, int M, int N, int K, co
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   GemmArgs args{M, N, K, e, col_base, m_fastest ? 1 : 0};
   args.reverse = tc_reverse();
+#ifdef BD_PDL
+  return launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, tmA, tmB, tmOut, tmOut2, args);
+#else
   kern<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, tmOut, tmOut2, args);
   return cudaGetLastError();
+#endif
 }
 
 cudaError_t gemm_tc_pair(const bf16* A, const bf16* W, int M, int N, int K, int epi, const GemmEpi& e, cudaStream_t s) {

@@ -59,6 +59,9 @@ struct Att2Args {
   int q_off;         // first query row handled by this kernel (rows [0, q_off) are done by attention_prefix_rows)
   float scale_log2;
   int reverse;       // walk the work items last-to-first (tc_set_reverse)
+#ifdef A2_NOMAX
+  float fixed_nmc;   // != 0: every score is known to satisfy s*scale_log2 <= -fixed_nmc, so the row maximum is not computed
+#endif
   long long* trace;  // debug: per-role clock64 stamps of CTA 0's first items (nullptr in production)
 };
 struct Att2Maps {    // Q, K: [BH*seq_pad, HD]; V^T: [BH*HD, seq_pad]; O: [L][seq][heads*HD] (3-D: rows are clipped at seq)
@@ -369,6 +372,12 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
             if (lane == 0) mbar_arrive(&s_free[g]);
           }
           if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 8 + 2);
+#ifdef A2_NOMAX   // bounded scores (q, k RMS-normalised): a constant offset replaces the running row maximum
+          const bool fixed = args.fixed_nmc != 0.0f;
+#else
+          constexpr bool fixed = false;
+#endif
+          if (!fixed) {
           float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
           for (int i = 0; i < BKV; i += 8) {
@@ -385,7 +394,12 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
             m_run = mx;
           }
           l_run *= alpha;
+          }
+#ifdef A2_NOMAX
+          float nmc = fixed ? args.fixed_nmc : -m_run * c;
+#else
           float nmc = -m_run * c;
+#endif
           float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
           if (turns) a2_turn_wait(g, nmc, turn_slot);
 #ifdef A2_TRACE_FINE   // two more stamps inside the exp phase (scripts/build_variant.sh fine attn_tc2.cu -DA2_TRACE_FINE): they cost ~2 %
@@ -430,6 +444,12 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (kv0 + c16 * 16 + i < seq) ? __uint_as_float(v[i]) : -INFINITY);
           }
+#ifdef A2_NOMAX
+          const bool fixed_t = args.fixed_nmc != 0.0f;
+#else
+          constexpr bool fixed_t = false;
+#endif
+          if (!fixed_t) {
           if (j == 0) {
             m_run = mx;
           } else if ((mx - m_run) * c > 8.0f) {
@@ -437,12 +457,17 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
             m_run = mx;
           }
           l_run *= alpha;
+          }
           if (j > 0) {
             mbar_wait(&pv_done[g], d_cnt & 1);
             ++d_cnt;
             tc_fence_after();
           }
+#ifdef A2_NOMAX
+          float nmc = fixed_t ? args.fixed_nmc : -m_run * c;
+#else
           float nmc = -m_run * c;
+#endif
           float psum = 0.f;
           if (turns) a2_turn_wait(g, nmc, turn_slot);
           for (int c16 = 0; c16 < n16; ++c16) {
@@ -538,6 +563,11 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
 }
 
 static int g_att2_sms = 0;
+#ifdef A2_NOMAX
+static thread_local float g_att2_fixed_nmc = 0.0f;
+// bound_log2 > 0: promise that every score times scale*log2(e) is <= bound_log2 for the next launches (0 switches back)
+void attention_tc2_set_score_bound(float bound_log2) { g_att2_fixed_nmc = (bound_log2 > 0.0f && bound_log2 < 60.0f) ? -bound_log2 : 0.0f; }
+#endif
 static long long* g_att2_trace = nullptr;
 void attention_tc2_set_trace(long long* dev_buf) { g_att2_trace = dev_buf; }
 
@@ -579,7 +609,11 @@ static cudaError_t launch_att2(const bf16* Q, const bf16* K, const bf16* Vt, bf1
   const int n_qt = (seq - q_off + A2_BQ - 1) / A2_BQ;
   const int n_items = BH * ((n_qt + 1) / 2);
   const int grid = n_items < g_att2_sms ? n_items : g_att2_sms;
+#ifdef A2_NOMAX
+  Att2Args a{heads, seq, seq_pad, BH, q_off, scale * 1.4426950408889634f, tc_reverse(), g_att2_fixed_nmc, g_att2_trace};
+#else
   Att2Args a{heads, seq, seq_pad, BH, q_off, scale * 1.4426950408889634f, tc_reverse(), g_att2_trace};
+#endif
 #ifdef BD_PDL
   return launch_pdl(kern, dim3(grid), dim3(A2_THREADS), Cfg::SMEM_BYTES, s, tm, a);
 #else

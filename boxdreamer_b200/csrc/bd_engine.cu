@@ -350,6 +350,26 @@ static cudaError_t linear(bd_engine* e, const void* in, const std::string& wname
   return gemm_f32(reinterpret_cast<const float*>(in), w.f32, M, N, K, epi, ep, s);
 }
 
+#ifdef A2_NOMAX
+namespace bd { void attention_tc2_set_score_bound(float bound_log2); }
+// |q.k| * scale <= sqrt(hd) * max|w_q| * max|w_k| for RMS-normalised q, k (blocks.py:44-56): log2 units, 2 % slack for bf16
+static float score_bound_log2(bd_engine* e, const std::string& p, int hd) {
+  static thread_local std::map<std::string, float> cache;   // per layer; weights are immutable after bd_finalize_weights
+  const std::string key = std::to_string(reinterpret_cast<uintptr_t>(e)) + p;
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  float wq[256], wk[256];
+  if (hd > 256) return 0.f;
+  if (cudaMemcpy(wq, WF(e, p + "attn.q_norm.weight"), hd * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 0.f;
+  if (cudaMemcpy(wk, WF(e, p + "attn.k_norm.weight"), hd * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 0.f;
+  float mq = 0.f, mk = 0.f;
+  for (int i = 0; i < hd; ++i) { mq = fmaxf(mq, fabsf(wq[i])); mk = fmaxf(mk, fabsf(wk[i])); }
+  const float b = 1.02f * sqrtf(static_cast<float>(hd)) * mq * mk * 1.4426950408889634f;
+  cache[key] = b;
+  return b;
+}
+#endif
+
 static cudaError_t attention(bd_engine* e, int L, int heads, int hd, int seq, int seq_pad, cudaStream_t s) {
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   if (e->tc)
@@ -384,7 +404,13 @@ static int run_block(bd_engine* e, float* X, const std::string& p, int L, int se
   BD_FLIP();
   LAUNCH(BD_PROF_GEMM_QKV, e->tc ? 1 : 2, linear(e, e->H, p + "attn.qkv.weight", M, 3 * d, d, EPI_QKV, q, s));
   BD_FLIP();
+#ifdef A2_NOMAX   // experimental (round 2); the bound is computed once per layer (one synchronous 768-byte copy at the first call)
+  if (qk_norm && e->tc) bd::attention_tc2_set_score_bound(score_bound_log2(e, p, hd));
+#endif
   LAUNCH(attn_cat, 1, attention(e, L, heads, hd, seq, seq_pad, s));
+#ifdef A2_NOMAX
+  bd::attention_tc2_set_score_bound(0.f);
+#endif
   GemmEpi pr;
   pr.bias = WF(e, p + "attn.proj.bias"); pr.out_f32 = X; pr.ldo = d; pr.gamma = g1 ? WF(e, p + g1) : nullptr;
   BD_FLIP();

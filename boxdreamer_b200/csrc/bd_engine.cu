@@ -71,6 +71,8 @@ struct bd_engine {
   cudaStream_t host_stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[8] = {nullptr};
+  cudaStream_t aux_stream = nullptr;   // BD_HALVES_OVERLAP: second pipeline (see run_layers)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // instrumentation: kernel launch counter and optional per-category CUDA-event timing
   long long launches = 0;
   int reverse = 0;  // traversal direction of the next kernel (L2 ping-pong, tc_set_reverse)
@@ -430,6 +432,84 @@ static int run_block(bd_engine* e, float* X, const std::string& p, int L, int se
   return BD_OK;
 }
 
+// ---- experimental, off by default (BD_HALVES_OVERLAP=1; prepared for round 2, not measured) --------------------------------
+// The transformer layers treat every image (encoder) / sample (decoder) independently, so the batch can run as two
+// independent pipelines on two streams over disjoint slices of the same workspace.  Two persistent tensor-core kernels
+// cannot share an SM (shared memory), so the GEMMs / attention of the two halves still serialise, but the HBM-bound kernels of
+// one half (LayerNorm: 3.6 ms of the step, not power-capped) can run underneath the tensor-bound kernels of the other half.
+struct BlockBufs { float* X; char* H; char* G; char* Q; char* K; char* V; char* O; };
+
+static int run_block_bufs(bd_engine* e, const BlockBufs& b, const std::string& p, int L, int seq, int seq_pad, int heads, int hd,
+                          float ln_eps, bool qk_norm, const char* g1, const char* g2, int attn_cat, cudaStream_t s) {
+  const int M = L * seq, d = e->d;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  LAUNCH(BD_PROF_LAYERNORM, 1, layernorm(b.X, WF(e, p + "norm1.weight"), WF(e, p + "norm1.bias"), ln_eps, nullptr,
+                                         reinterpret_cast<bf16*>(b.H), M, d, 0, 0, 0, s));
+  GemmEpi q;
+  q.bias = WF(e, p + "attn.qkv.bias");
+  q.q = b.Q; q.k = b.K; q.v = b.V;
+  q.q_norm_w = qk_norm ? WF(e, p + "attn.q_norm.weight") : nullptr;
+  q.k_norm_w = qk_norm ? WF(e, p + "attn.k_norm.weight") : nullptr;
+  q.seq = seq; q.seq_pad = seq_pad; q.heads = heads; q.head_dim = hd; q.rms_eps = 1e-6f;
+  LAUNCH(BD_PROF_GEMM_QKV, 1, gemm_tc(reinterpret_cast<const bf16*>(b.H), e->w[p + "attn.qkv.weight"].b16, M, 3 * d, d, EPI_QKV, q, s));
+  LAUNCH(attn_cat, 1, attention_tc(reinterpret_cast<const bf16*>(b.Q), reinterpret_cast<const bf16*>(b.K), reinterpret_cast<const bf16*>(b.V),
+                                   reinterpret_cast<bf16*>(b.O), L, heads, hd, seq, seq_pad, scale, e->cfg.attn_variant, s));
+  GemmEpi pr;
+  pr.bias = WF(e, p + "attn.proj.bias"); pr.out_f32 = b.X; pr.ldo = d; pr.gamma = g1 ? WF(e, p + g1) : nullptr;
+  LAUNCH(BD_PROF_GEMM_PROJ, 1, gemm_tc(reinterpret_cast<const bf16*>(b.O), e->w[p + "attn.proj.weight"].b16, M, d, d, EPI_RESID, pr, s));
+  LAUNCH(BD_PROF_LAYERNORM, 1, layernorm(b.X, WF(e, p + "norm2.weight"), WF(e, p + "norm2.bias"), ln_eps, nullptr,
+                                         reinterpret_cast<bf16*>(b.H), M, d, 0, 0, 0, s));
+  GemmEpi f1;
+  f1.bias = WF(e, p + "mlp.fc1.bias"); f1.out_act = b.G;
+  LAUNCH(BD_PROF_GEMM_FC1, 1, gemm_tc(reinterpret_cast<const bf16*>(b.H), e->w[p + "mlp.fc1.weight"].b16, M, 4 * d, d, EPI_GELU, f1, s));
+  GemmEpi f2;
+  f2.bias = WF(e, p + "mlp.fc2.bias"); f2.out_f32 = b.X; f2.ldo = d; f2.gamma = g2 ? WF(e, p + g2) : nullptr;
+  LAUNCH(BD_PROF_GEMM_FC2, 1, gemm_tc(reinterpret_cast<const bf16*>(b.G), e->w[p + "mlp.fc2.weight"].b16, M, d, 4 * d, EPI_RESID, f2, s));
+  return BD_OK;
+}
+
+static bool halves_overlap_enabled() {
+  static const bool on = getenv("BD_HALVES_OVERLAP") && atoi(getenv("BD_HALVES_OVERLAP")) != 0;
+  return on;
+}
+
+// all `layers` blocks "<prefix><i>." over L sequences of `seq` tokens: one pipeline, or two halves on two streams
+static int run_layers(bd_engine* e, float* X, const std::string& prefix, int layers, int L, int seq, int seq_pad, int heads, int hd,
+                      float ln_eps, bool qk_norm, const char* g1, const char* g2, int attn_cat, cudaStream_t s) {
+  if (!(e->tc && halves_overlap_enabled() && L >= 2)) {
+    for (int i = 0; i < layers; ++i) {
+      int r = run_block(e, X, prefix + std::to_string(i) + ".", L, seq, seq_pad, heads, hd, ln_eps, qk_norm, g1, g2, attn_cat, s);
+      if (r != BD_OK) return r;
+    }
+    return BD_OK;
+  }
+  if (!e->aux_stream) {
+    CK(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  }
+  const int d = e->d;
+  const int Lh[2] = {L / 2, L - L / 2};
+  CK(cudaEventRecord(e->ev_fork, s));
+  CK(cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+  for (int h = 0; h < 2; ++h) {
+    cudaStream_t sh = h == 0 ? s : e->aux_stream;
+    const size_t l0 = h == 0 ? 0 : static_cast<size_t>(Lh[0]);
+    const size_t row0 = l0 * seq;
+    const size_t qk0 = l0 * heads * static_cast<size_t>(seq_pad) * hd * 2;   // bf16 Q / K / V^T: [L*heads, seq_pad, hd] elements
+    BlockBufs b{X + row0 * d, static_cast<char*>(e->H) + row0 * d * 2, static_cast<char*>(e->G) + row0 * 4 * d * 2,
+                static_cast<char*>(e->Q) + qk0, static_cast<char*>(e->K) + qk0, static_cast<char*>(e->V) + qk0,
+                static_cast<char*>(e->O) + row0 * d * 2};
+    for (int i = 0; i < layers; ++i) {
+      int r = run_block_bufs(e, b, prefix + std::to_string(i) + ".", Lh[h], seq, seq_pad, heads, hd, ln_eps, qk_norm, g1, g2, attn_cat, sh);
+      if (r != BD_OK) return r;
+    }
+  }
+  CK(cudaEventRecord(e->ev_join, e->aux_stream));
+  CK(cudaStreamWaitEvent(s, e->ev_join, 0));
+  return BD_OK;
+}
+
 // `out_img_off`: first image slot of feats_out / feats_act this call writes (the host-buffer entry runs the encoder in chunks
 // while later images are still in flight); feats_out may be null on the tensor path (only the bf16 copy is consumed then).
 static int dino_forward_impl(bd_engine* e, const void* images, int dtype, float* feats_out, int L, cudaStream_t s, int out_img_off = 0) {
@@ -446,9 +526,9 @@ static int dino_forward_impl(bd_engine* e, const void* images, int dtype, float*
   LAUNCH(BD_PROF_GEMM_OTHER, 1, linear(e, e->A_pe, "dino.patch_embed.proj.weight", L * P, d, e->kpe, EPI_F32, pe, s));
   LAUNCH(BD_PROF_GLUE, 1, dino_prefix_tokens(e->X_dino, WF(e, "dino.cls_token"), WF(e, "dino.pos_embed"),
                                              WF(e, "dino.register_tokens"), L, e->n_tok, e->cfg.dino_registers, d, s));
-  for (int i = 0; i < e->cfg.dino_layers; ++i) {
-    int r = run_block(e, e->X_dino, "dino.blocks." + std::to_string(i) + ".", L, e->n_tok, e->seqpad_dino, e->cfg.dino_heads,
-                      e->hd_dino, 1e-6f, false, "ls1.gamma", "ls2.gamma", BD_PROF_ATTENTION_DINO, s);
+  {
+    int r = run_layers(e, e->X_dino, "dino.blocks.", e->cfg.dino_layers, L, e->n_tok, e->seqpad_dino, e->cfg.dino_heads, e->hd_dino, 1e-6f,
+                       false, "ls1.gamma", "ls2.gamma", BD_PROF_ATTENTION_DINO, s);
     if (r != BD_OK) return r;
   }
   // final LayerNorm, patch tokens only (vision_transformer.py:263-267)
@@ -485,9 +565,9 @@ static int decoder_forward_impl(bd_engine* e, const void* bbox_feat, int dtype, 
   LAUNCH(BD_PROF_GEMM_OTHER, 1, linear(e, e->A_bb, "decoder.bbox_emb.weight", M, d, pp8, EPI_F32, be, s));
   LAUNCH(BD_PROF_GLUE, 1, betr_fuse(e->PF, e->R, WF(e, "decoder.bbox_learnable_query"), e->pos_dec, query_idx, e->X_dec, B, T, P, d, 1e-6f, s));
   const int seq = T * P, seq_pad = (seq + 127) / 128 * 128;
-  for (int i = 0; i < e->cfg.dec_layers; ++i) {
-    int r = run_block(e, e->X_dec, "decoder.attn." + std::to_string(i) + ".", B, seq, seq_pad, e->cfg.dec_heads, e->hd_dec, 1e-5f,
-                      true, nullptr, nullptr, BD_PROF_ATTENTION, s);
+  {
+    int r = run_layers(e, e->X_dec, "decoder.attn.", e->cfg.dec_layers, B, seq, seq_pad, e->cfg.dec_heads, e->hd_dec, 1e-5f, true, nullptr,
+                       nullptr, BD_PROF_ATTENTION, s);
     if (r != BD_OK) return r;
   }
   LAUNCH(BD_PROF_GLUE, 1, gather_query(e->X_dec, query_idx, e->tc ? nullptr : reinterpret_cast<float*>(e->Xq),

@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libboxdreamer_b200.so")
-SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "attn_tc.cu", "attn_tc2.cu", "kernels_simt.cu", "post.cu", "bd_engine.cu"]
+SOURCES = ["tc_host.cu", "gemm_tc2.cu", "attn_tc2.cu", "kernels_simt.cu", "post.cu", "bd_engine.cu"]
 HEADERS = ["common.cuh", "bd_internal.h", "gemm_epi.cuh", os.path.join("..", "..", "include", "boxdreamer_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -1,6 +1,8 @@
-// Attention v2: persistent, two query tiles per CTA in ping-pong (sm_100a, tcgen05 + TMEM + TMA).
+// Attention: persistent, two query tiles per CTA in ping-pong (sm_100a, tcgen05 + TMEM + TMA).
 //
-// Same operand layouts and math as attn_tc.cu (Q,K [BH, seq_pad, HD]; V^T [BH, HD, seq_pad]; O token-major), but
+// Replaces flash_attn_func / F.scaled_dot_product_attention at blocks.py:259-285 (decoder, 8 heads x 96) and the DINOv2
+// attention (layers/attention.py:56-69, 12 heads x 64).  Operand layouts: Q, K [BH, seq_pad, HD]; V^T [BH, HD, seq_pad]; O
+// token-major [L*seq, heads*HD] (written by the QKV GEMM epilogue / read by the proj GEMM).
 //   * one persistent CTA per SM walks (bh, 256-row query pair) work items: TMEM (512 columns), barriers and tensor-map
 //     prefetch are set up once, K/V tiles stream through an smem ring across items;
 //   * two 128-row query tiles share every K/V tile; the MMA warp interleaves  S0, S1, PV0, S0', PV1, S1', ...  so one
@@ -33,6 +35,39 @@ static constexpr int A2_CTRL_WARP = 8;
 #define A2_PASS_DEN 4
 #endif
 static constexpr int A2_BQ = 128;
+// One quad of scores in A2_POLY_PERIOD goes through ex2_poly_pair (FMA pipe) instead of the MUFU pipe; 0 = all on MUFU.
+// Measured on B200 (decoder shape, isolated / in-step ms per launch): 0 -> 0.4426 / 0.545; 4 -> 0.4386 / 0.510; 3 -> 0.4491; 2 -> 0.4762
+// (profiles/r02_attention_variants.txt).  A2_PACK2: scale the scores with packed FFMA2 (needed for the polynomial to pay: the
+// issue port, not only the MUFU pipe, limits the exp loop).
+#ifndef A2_POLY_PERIOD
+#define A2_POLY_PERIOD 4
+#define A2_PACK2 1
+#endif
+#ifndef A2_POLY_PHASE
+#define A2_POLY_PHASE (A2_POLY_PERIOD - 1)
+#endif
+
+// 2^x for a pair of scores on the FMA pipe (packed fp32): x = s*c + nmc, clamped at -126, split into n = round(x) and
+// f = x - n in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, far below the bf16 rounding of P);
+// n goes straight into the exponent field.
+__device__ __forceinline__ void ex2_poly_pair(float s0, float s1, f32x2 cc, f32x2 nn, float& r0, float& r1) {
+  float x0, x1;
+  unpack_f32x2(fma_f32x2(pack_f32x2(s0, s1), cc, nn), x0, x1);
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const f32x2 x = pack_f32x2(x0, x1);
+  const f32x2 t = add_f32x2(x, pack_f32x2(12582912.0f, 12582912.0f));            // 1.5 * 2^23: the low mantissa bits hold round(x)
+  const f32x2 n = add_f32x2(t, pack_f32x2(-12582912.0f, -12582912.0f));
+  const f32x2 f = fma_f32x2(n, pack_f32x2(-1.0f, -1.0f), x);
+  f32x2 p = fma_f32x2(f, pack_f32x2(0.0551716685f, 0.0551716685f), pack_f32x2(0.2426111251f, 0.2426111251f));
+  p = fma_f32x2(p, f, pack_f32x2(0.6932609677f, 0.6932609677f));
+  p = fma_f32x2(p, f, pack_f32x2(0.9999280572f, 0.9999280572f));
+  float pa, pb, ta, tb;
+  unpack_f32x2(p, pa, pb);
+  unpack_f32x2(t, ta, tb);
+  r0 = __uint_as_float(__float_as_uint(pa) + (__float_as_uint(ta) << 23));
+  r1 = __uint_as_float(__float_as_uint(pb) + (__float_as_uint(tb) << 23));
+}
 
 template <int HD>
 struct Att2Cfg {
@@ -58,10 +93,6 @@ struct Att2Args {
   int heads, seq, seq_pad, BH;
   int q_off;         // first query row handled by this kernel (rows [0, q_off) are done by attention_prefix_rows)
   float scale_log2;
-  int reverse;       // walk the work items last-to-first (tc_set_reverse)
-#ifdef A2_NOMAX
-  float fixed_nmc;   // != 0: every score is known to satisfy s*scale_log2 <= -fixed_nmc, so the row maximum is not computed
-#endif
   long long* trace;  // debug: per-role clock64 stamps of CTA 0's first items (nullptr in production)
 };
 struct Att2Maps {    // Q, K: [BH*seq_pad, HD]; V^T: [BH*HD, seq_pad]; O: [L][seq][heads*HD] (3-D: rows are clipped at seq)
@@ -177,11 +208,9 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
     tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
-  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_wait();   // (BD_PDL builds) everything above overlapped the predecessor's tail; no global access before this point
   // broadcast through a shuffle so the compiler keeps the TMEM base (and everything derived from it) in uniform registers
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
@@ -194,7 +223,7 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
     uint32_t ph = 0;
     int it = 0;
     for (int item_f = blockIdx.x; item_f < n_items; item_f += gridDim.x, ++it) {
-      const int item = args.reverse ? n_items - 1 - item_f : item_f;
+      const int item = item_f;
       const int bh = item / n_pairs, pair = item % n_pairs;
       const int q0 = q_off + pair * 2 * A2_BQ;
       const bool act1 = q0 + A2_BQ < seq;
@@ -242,7 +271,7 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
     // PV0(j) PV1(j).  S(j+1) is therefore already complete when a group finishes tile j: the groups never wait for the
     // tensor pipe in steady state and the kernel runs at the pace of the exp (MUFU) pipe.
     for (int item_f = blockIdx.x; item_f < n_items; item_f += gridDim.x, ++it) {
-      const int item = args.reverse ? n_items - 1 - item_f : item_f;
+      const int item = item_f;
       const int pair = item % n_pairs;
       const bool act1 = q_off + pair * 2 * A2_BQ + A2_BQ < seq;
       const int qb = it % QBUF;
@@ -332,7 +361,7 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
     int pend_qb = -1, pend_arrivals = 0;    // O store in flight out of Q buffer pend_qb (storer thread only)
     int it = 0;
     for (int item_f = blockIdx.x; item_f < n_items; item_f += gridDim.x, ++it) {
-      const int item = args.reverse ? n_items - 1 - item_f : item_f;
+      const int item = item_f;
       const int bh = item / n_pairs, pair = item % n_pairs;
       const int q0 = q_off + pair * 2 * A2_BQ + g * A2_BQ;
       if (q0 >= seq) {  // inactive second tile: the whole group skips this item (but still releases its last staging tile:
@@ -372,12 +401,6 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
             if (lane == 0) mbar_arrive(&s_free[g]);
           }
           if (quad == 0 && lane == 0) A2_TRACE(1 + g, (it * n_kv + j) * 8 + 2);
-#ifdef A2_NOMAX   // bounded scores (q, k RMS-normalised): a constant offset replaces the running row maximum
-          const bool fixed = args.fixed_nmc != 0.0f;
-#else
-          constexpr bool fixed = false;
-#endif
-          if (!fixed) {
           float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
           for (int i = 0; i < BKV; i += 8) {
@@ -394,12 +417,7 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
             m_run = mx;
           }
           l_run *= alpha;
-          }
-#ifdef A2_NOMAX
-          float nmc = fixed ? args.fixed_nmc : -m_run * c;
-#else
           float nmc = -m_run * c;
-#endif
           float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
           if (turns) a2_turn_wait(g, nmc, turn_slot);
 #ifdef A2_TRACE_FINE   // two more stamps inside the exp phase (scripts/build_variant.sh fine attn_tc2.cu -DA2_TRACE_FINE): they cost ~2 %
@@ -408,14 +426,35 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
           // The turn is handed over when A2_PASS_NUM/A2_PASS_DEN of the exponentials are done: the other group's first
           // exponentials overlap this group's last ones, which hides the hand-over latency without starving the MUFU pipe.
           constexpr int PASS_I = ((BKV / 2) * A2_PASS_NUM / A2_PASS_DEN) & ~1;
+#if A2_POLY_PERIOD > 0 || defined(A2_PACK2)
+          const f32x2 cc2 = pack_f32x2(c, c), nn2 = pack_f32x2(nmc, nmc);
+#endif
 #pragma unroll
           for (int i = 0; i < BKV / 2; i += 2) {
             if (i == PASS_I && turns && !(g == 1 && last))   // group 1's last pass of an item is replaced by the next item's opening pass
               a2_turn_pass(g, (ps0 + ps1) + (ps2 + ps3), turn_slot + 1024);
-            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), c, nmc));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), c, nmc));
-            const float p2 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 2]), c, nmc));
-            const float p3 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 3]), c, nmc));
+            float p0, p1, p2, p3;
+#if A2_POLY_PERIOD > 0
+            // every A2_POLY_PERIOD-th quad of scores takes the FMA-pipe polynomial instead of the MUFU pipe (the MUFU pipe is
+            // the kernel's bound: 16 ex2 per clock and SM against 2 x 128 x BKV exponentials per key-tile pair)
+            if (((i >> 1) % A2_POLY_PERIOD) == A2_POLY_PHASE) {
+              ex2_poly_pair(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1]), cc2, nn2, p0, p1);
+              ex2_poly_pair(__uint_as_float(sv[2 * i + 2]), __uint_as_float(sv[2 * i + 3]), cc2, nn2, p2, p3);
+            } else
+#endif
+            {
+#ifdef A2_PACK2
+              float x0, x1, x2, x3;
+              unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), cc2, nn2), x0, x1);
+              unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * i + 2]), __uint_as_float(sv[2 * i + 3])), cc2, nn2), x2, x3);
+              p0 = ex2_approx(x0); p1 = ex2_approx(x1); p2 = ex2_approx(x2); p3 = ex2_approx(x3);
+#else
+              p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), c, nmc));
+              p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), c, nmc));
+              p2 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 2]), c, nmc));
+              p3 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 3]), c, nmc));
+#endif
+            }
             ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
             sv[i] = pack_bf16x2(p0, p1);       // in place: word i is written after elements 2i, 2i+1 were consumed
             sv[i + 1] = pack_bf16x2(p2, p3);
@@ -444,12 +483,6 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (kv0 + c16 * 16 + i < seq) ? __uint_as_float(v[i]) : -INFINITY);
           }
-#ifdef A2_NOMAX
-          const bool fixed_t = args.fixed_nmc != 0.0f;
-#else
-          constexpr bool fixed_t = false;
-#endif
-          if (!fixed_t) {
           if (j == 0) {
             m_run = mx;
           } else if ((mx - m_run) * c > 8.0f) {
@@ -457,17 +490,12 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
             m_run = mx;
           }
           l_run *= alpha;
-          }
           if (j > 0) {
             mbar_wait(&pv_done[g], d_cnt & 1);
             ++d_cnt;
             tc_fence_after();
           }
-#ifdef A2_NOMAX
-          float nmc = fixed_t ? args.fixed_nmc : -m_run * c;
-#else
           float nmc = -m_run * c;
-#endif
           float psum = 0.f;
           if (turns) a2_turn_wait(g, nmc, turn_slot);
           for (int c16 = 0; c16 < n16; ++c16) {
@@ -562,12 +590,6 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
   }
 }
 
-static int g_att2_sms = 0;
-#ifdef A2_NOMAX
-static thread_local float g_att2_fixed_nmc = 0.0f;
-// bound_log2 > 0: promise that every score times scale*log2(e) is <= bound_log2 for the next launches (0 switches back)
-void attention_tc2_set_score_bound(float bound_log2) { g_att2_fixed_nmc = (bound_log2 > 0.0f && bound_log2 < 60.0f) ? -bound_log2 : 0.0f; }
-#endif
 static long long* g_att2_trace = nullptr;
 void attention_tc2_set_trace(long long* dev_buf) { g_att2_trace = dev_buf; }
 
@@ -595,31 +617,15 @@ static cudaError_t launch_att2(const bf16* Q, const bf16* K, const bf16* Vt, bf1
   else if (ok) tm.v2 = tm.v;
   if (!ok) return cudaErrorInvalidValue;
   auto kern = attn_tc2_kernel<HD>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (err != cudaSuccess) return err;
-    attr_set = true;
-  }
-  if (g_att2_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_att2_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  cudaError_t aerr = tc_ensure_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES);
+  if (aerr != cudaSuccess) return aerr;
+  const int n_sms = tc_num_sms();
   const int n_qt = (seq - q_off + A2_BQ - 1) / A2_BQ;
   const int n_items = BH * ((n_qt + 1) / 2);
-  const int grid = n_items < g_att2_sms ? n_items : g_att2_sms;
-#ifdef A2_NOMAX
-  Att2Args a{heads, seq, seq_pad, BH, q_off, scale * 1.4426950408889634f, tc_reverse(), g_att2_fixed_nmc, g_att2_trace};
-#else
-  Att2Args a{heads, seq, seq_pad, BH, q_off, scale * 1.4426950408889634f, tc_reverse(), g_att2_trace};
-#endif
-#ifdef BD_PDL
-  return launch_pdl(kern, dim3(grid), dim3(A2_THREADS), Cfg::SMEM_BYTES, s, tm, a);
-#else
+  const int grid = n_items < n_sms ? n_items : n_sms;
+  Att2Args a{heads, seq, seq_pad, BH, q_off, scale * 1.4426950408889634f, g_att2_trace};
   kern<<<grid, A2_THREADS, Cfg::SMEM_BYTES, s>>>(tm, a);
   return cudaGetLastError();
-#endif
 }
 
 // Rows [0, nrows) (nrows <= 8) of every sequence: one WARP per (image, head), flash-style over 96-key chunks with
@@ -651,8 +657,6 @@ __global__ void __launch_bounds__(PFX_WARPS * 32) attention_prefix_rows_kernel(c
   constexpr int OT = HD / 8;           // 8-dim output tiles
   const int lane = threadIdx.x & 31;
   const int bh = blockIdx.x * PFX_WARPS + (threadIdx.x >> 5);
-  pdl_launch_dependents();
-  pdl_wait();
   if (bh >= BH) return;
   const int g = lane >> 2, q = lane & 3;
   const bf16* Qb = Q + static_cast<long long>(bh) * seq_pad * HD;
@@ -746,17 +750,12 @@ static cudaError_t launch_prefix(const bf16* Q, const bf16* K, const bf16* Vt, b
   const float sl = scale * 1.4426950408889634f;
   const int BH = L * heads;
   note_extra_launches(1);
-#ifdef BD_PDL
-  return launch_pdl(attention_prefix_rows_kernel<HD>, dim3((BH + PFX_WARPS - 1) / PFX_WARPS), dim3(PFX_WARPS * 32), 0, s, Q, K, Vt, O, BH, heads, seq,
-                    seq_pad, nrows, sl);
-#else
   attention_prefix_rows_kernel<HD><<<(BH + PFX_WARPS - 1) / PFX_WARPS, PFX_WARPS * 32, 0, s>>>(Q, K, Vt, O, BH, heads, seq, seq_pad, nrows, sl);
   return cudaGetLastError();
-#endif
 }
 
-cudaError_t attention_tc2(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int head_dim, int seq,
-                          int seq_pad, float scale, cudaStream_t s) {
+cudaError_t attention_tc(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int head_dim, int seq,
+                         int seq_pad, float scale, cudaStream_t s) {
   if (seq_pad % 128 != 0 || seq > seq_pad || seq <= 0) return cudaErrorInvalidValue;
   // a handful of rows beyond a multiple of 128 (DINOv2: 5 + 256) would cost a whole extra query tile: peel them off
   const int rem = seq % A2_BQ;

@@ -71,11 +71,8 @@ struct bd_engine {
   cudaStream_t host_stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[8] = {nullptr};
-  cudaStream_t aux_stream = nullptr;   // BD_HALVES_OVERLAP: second pipeline (see run_layers)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // instrumentation: kernel launch counter and optional per-category CUDA-event timing
   long long launches = 0;
-  int reverse = 0;  // traversal direction of the next kernel (L2 ping-pong, tc_set_reverse)
   bool profile = false;
   struct Span { int cat; cudaEvent_t a, b; };
   std::vector<Span> spans;
@@ -159,7 +156,6 @@ extern "C" int bd_create(bd_handle* out, const bd_config* cfg) {
     delete e;
     return fail(BD_ERR_UNSUPPORTED, "bd_create: the bf16 tensor path needs an sm_100 (Blackwell) device");
   }
-  tc_set_num_sms(prop.multiProcessorCount);
   e->S = cfg->img_size; e->patch = cfg->patch_size; e->g = e->S / e->patch; e->P = e->g * e->g; e->d = cfg->d_model;
   e->hd_dec = e->d / cfg->dec_heads; e->hd_dino = e->d / cfg->dino_heads;
   e->n_prefix = 1 + cfg->dino_registers; e->n_tok = e->n_prefix + e->P;
@@ -352,31 +348,11 @@ static cudaError_t linear(bd_engine* e, const void* in, const std::string& wname
   return gemm_f32(reinterpret_cast<const float*>(in), w.f32, M, N, K, epi, ep, s);
 }
 
-#ifdef A2_NOMAX
-namespace bd { void attention_tc2_set_score_bound(float bound_log2); }
-// |q.k| * scale <= sqrt(hd) * max|w_q| * max|w_k| for RMS-normalised q, k (blocks.py:44-56): log2 units, 2 % slack for bf16
-static float score_bound_log2(bd_engine* e, const std::string& p, int hd) {
-  static thread_local std::map<std::string, float> cache;   // per layer; weights are immutable after bd_finalize_weights
-  const std::string key = std::to_string(reinterpret_cast<uintptr_t>(e)) + p;
-  auto it = cache.find(key);
-  if (it != cache.end()) return it->second;
-  float wq[256], wk[256];
-  if (hd > 256) return 0.f;
-  if (cudaMemcpy(wq, WF(e, p + "attn.q_norm.weight"), hd * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 0.f;
-  if (cudaMemcpy(wk, WF(e, p + "attn.k_norm.weight"), hd * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 0.f;
-  float mq = 0.f, mk = 0.f;
-  for (int i = 0; i < hd; ++i) { mq = fmaxf(mq, fabsf(wq[i])); mk = fmaxf(mk, fabsf(wk[i])); }
-  const float b = 1.02f * sqrtf(static_cast<float>(hd)) * mq * mk * 1.4426950408889634f;
-  cache[key] = b;
-  return b;
-}
-#endif
-
 static cudaError_t attention(bd_engine* e, int L, int heads, int hd, int seq, int seq_pad, cudaStream_t s) {
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   if (e->tc)
     return attention_tc(reinterpret_cast<const bf16*>(e->Q), reinterpret_cast<const bf16*>(e->K), reinterpret_cast<const bf16*>(e->V),
-                        reinterpret_cast<bf16*>(e->O), L, heads, hd, seq, seq_pad, scale, e->cfg.attn_variant, s);
+                        reinterpret_cast<bf16*>(e->O), L, heads, hd, seq, seq_pad, scale, s);
   return attention_f32(reinterpret_cast<const float*>(e->Q), reinterpret_cast<const float*>(e->K),
                        reinterpret_cast<const float*>(e->V), reinterpret_cast<float*>(e->O), L, heads, hd, seq, seq_pad, scale, s);
 }
@@ -390,12 +366,6 @@ static cudaError_t ln_act(bd_engine* e, const float* x, const float* w, const fl
 static int run_block(bd_engine* e, float* X, const std::string& p, int L, int seq, int seq_pad, int heads, int hd, float ln_eps,
                      bool qk_norm, const char* g1, const char* g2, int attn_cat, cudaStream_t s) {
   const int M = L * seq, d = e->d;
-  // L2 ping-pong (BD_L2_PINGPONG=1): consecutive kernels walk their rows / tiles / items in opposite directions
-  // (tc_set_reverse).  Measured on B200 at BASELINE config 2: every kernel gets 2-4 % shorter under the event profile, but
-  // the step is power-capped and the SM clock drops by the same amount -- no gain end to end, so it is off by default.
-  static const bool pingpong = getenv("BD_L2_PINGPONG") && atoi(getenv("BD_L2_PINGPONG")) != 0;
-#define BD_FLIP() do { if (pingpong) { e->reverse ^= 1; tc_set_reverse(e->reverse); } } while (0)
-  BD_FLIP();
   LAUNCH(BD_PROF_LAYERNORM, 1, ln_act(e, X, WF(e, p + "norm1.weight"), WF(e, p + "norm1.bias"), ln_eps, M, s));
   GemmEpi q;
   q.bias = WF(e, p + "attn.qkv.bias");
@@ -403,110 +373,28 @@ static int run_block(bd_engine* e, float* X, const std::string& p, int L, int se
   q.q_norm_w = qk_norm ? WF(e, p + "attn.q_norm.weight") : nullptr;
   q.k_norm_w = qk_norm ? WF(e, p + "attn.k_norm.weight") : nullptr;
   q.seq = seq; q.seq_pad = seq_pad; q.heads = heads; q.head_dim = hd; q.rms_eps = 1e-6f;
-  BD_FLIP();
   LAUNCH(BD_PROF_GEMM_QKV, e->tc ? 1 : 2, linear(e, e->H, p + "attn.qkv.weight", M, 3 * d, d, EPI_QKV, q, s));
-  BD_FLIP();
-#ifdef A2_NOMAX   // experimental (round 2); the bound is computed once per layer (one synchronous 768-byte copy at the first call)
-  if (qk_norm && e->tc) bd::attention_tc2_set_score_bound(score_bound_log2(e, p, hd));
-#endif
   LAUNCH(attn_cat, 1, attention(e, L, heads, hd, seq, seq_pad, s));
-#ifdef A2_NOMAX
-  bd::attention_tc2_set_score_bound(0.f);
-#endif
   GemmEpi pr;
   pr.bias = WF(e, p + "attn.proj.bias"); pr.out_f32 = X; pr.ldo = d; pr.gamma = g1 ? WF(e, p + g1) : nullptr;
-  BD_FLIP();
   LAUNCH(BD_PROF_GEMM_PROJ, 1, linear(e, e->O, p + "attn.proj.weight", M, d, d, EPI_RESID, pr, s));
-  BD_FLIP();
   LAUNCH(BD_PROF_LAYERNORM, 1, ln_act(e, X, WF(e, p + "norm2.weight"), WF(e, p + "norm2.bias"), ln_eps, M, s));
   GemmEpi f1;
   f1.bias = WF(e, p + "mlp.fc1.bias"); f1.out_act = e->G;
-  BD_FLIP();
   LAUNCH(BD_PROF_GEMM_FC1, 1, linear(e, e->H, p + "mlp.fc1.weight", M, 4 * d, d, EPI_GELU, f1, s));
   GemmEpi f2;
   f2.bias = WF(e, p + "mlp.fc2.bias"); f2.out_f32 = X; f2.ldo = d; f2.gamma = g2 ? WF(e, p + g2) : nullptr;
-  BD_FLIP();
   LAUNCH(BD_PROF_GEMM_FC2, 1, linear(e, e->G, p + "mlp.fc2.weight", M, d, 4 * d, EPI_RESID, f2, s));
-  tc_set_reverse(0);
-#undef BD_FLIP
   return BD_OK;
 }
 
-// ---- experimental, off by default (BD_HALVES_OVERLAP=1; prepared for round 2, not measured) --------------------------------
-// The transformer layers treat every image (encoder) / sample (decoder) independently, so the batch can run as two
-// independent pipelines on two streams over disjoint slices of the same workspace.  Two persistent tensor-core kernels
-// cannot share an SM (shared memory), so the GEMMs / attention of the two halves still serialise, but the HBM-bound kernels of
-// one half (LayerNorm: 3.6 ms of the step, not power-capped) can run underneath the tensor-bound kernels of the other half.
-struct BlockBufs { float* X; char* H; char* G; char* Q; char* K; char* V; char* O; };
-
-static int run_block_bufs(bd_engine* e, const BlockBufs& b, const std::string& p, int L, int seq, int seq_pad, int heads, int hd,
-                          float ln_eps, bool qk_norm, const char* g1, const char* g2, int attn_cat, cudaStream_t s) {
-  const int M = L * seq, d = e->d;
-  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
-  LAUNCH(BD_PROF_LAYERNORM, 1, layernorm(b.X, WF(e, p + "norm1.weight"), WF(e, p + "norm1.bias"), ln_eps, nullptr,
-                                         reinterpret_cast<bf16*>(b.H), M, d, 0, 0, 0, s));
-  GemmEpi q;
-  q.bias = WF(e, p + "attn.qkv.bias");
-  q.q = b.Q; q.k = b.K; q.v = b.V;
-  q.q_norm_w = qk_norm ? WF(e, p + "attn.q_norm.weight") : nullptr;
-  q.k_norm_w = qk_norm ? WF(e, p + "attn.k_norm.weight") : nullptr;
-  q.seq = seq; q.seq_pad = seq_pad; q.heads = heads; q.head_dim = hd; q.rms_eps = 1e-6f;
-  LAUNCH(BD_PROF_GEMM_QKV, 1, gemm_tc(reinterpret_cast<const bf16*>(b.H), e->w[p + "attn.qkv.weight"].b16, M, 3 * d, d, EPI_QKV, q, s));
-  LAUNCH(attn_cat, 1, attention_tc(reinterpret_cast<const bf16*>(b.Q), reinterpret_cast<const bf16*>(b.K), reinterpret_cast<const bf16*>(b.V),
-                                   reinterpret_cast<bf16*>(b.O), L, heads, hd, seq, seq_pad, scale, e->cfg.attn_variant, s));
-  GemmEpi pr;
-  pr.bias = WF(e, p + "attn.proj.bias"); pr.out_f32 = b.X; pr.ldo = d; pr.gamma = g1 ? WF(e, p + g1) : nullptr;
-  LAUNCH(BD_PROF_GEMM_PROJ, 1, gemm_tc(reinterpret_cast<const bf16*>(b.O), e->w[p + "attn.proj.weight"].b16, M, d, d, EPI_RESID, pr, s));
-  LAUNCH(BD_PROF_LAYERNORM, 1, layernorm(b.X, WF(e, p + "norm2.weight"), WF(e, p + "norm2.bias"), ln_eps, nullptr,
-                                         reinterpret_cast<bf16*>(b.H), M, d, 0, 0, 0, s));
-  GemmEpi f1;
-  f1.bias = WF(e, p + "mlp.fc1.bias"); f1.out_act = b.G;
-  LAUNCH(BD_PROF_GEMM_FC1, 1, gemm_tc(reinterpret_cast<const bf16*>(b.H), e->w[p + "mlp.fc1.weight"].b16, M, 4 * d, d, EPI_GELU, f1, s));
-  GemmEpi f2;
-  f2.bias = WF(e, p + "mlp.fc2.bias"); f2.out_f32 = b.X; f2.ldo = d; f2.gamma = g2 ? WF(e, p + g2) : nullptr;
-  LAUNCH(BD_PROF_GEMM_FC2, 1, gemm_tc(reinterpret_cast<const bf16*>(b.G), e->w[p + "mlp.fc2.weight"].b16, M, d, 4 * d, EPI_RESID, f2, s));
-  return BD_OK;
-}
-
-static bool halves_overlap_enabled() {
-  static const bool on = getenv("BD_HALVES_OVERLAP") && atoi(getenv("BD_HALVES_OVERLAP")) != 0;
-  return on;
-}
-
-// all `layers` blocks "<prefix><i>." over L sequences of `seq` tokens: one pipeline, or two halves on two streams
+// all `layers` blocks "<prefix><i>." over L sequences of `seq` tokens
 static int run_layers(bd_engine* e, float* X, const std::string& prefix, int layers, int L, int seq, int seq_pad, int heads, int hd,
                       float ln_eps, bool qk_norm, const char* g1, const char* g2, int attn_cat, cudaStream_t s) {
-  if (!(e->tc && halves_overlap_enabled() && L >= 2)) {
-    for (int i = 0; i < layers; ++i) {
-      int r = run_block(e, X, prefix + std::to_string(i) + ".", L, seq, seq_pad, heads, hd, ln_eps, qk_norm, g1, g2, attn_cat, s);
-      if (r != BD_OK) return r;
-    }
-    return BD_OK;
+  for (int i = 0; i < layers; ++i) {
+    int r = run_block(e, X, prefix + std::to_string(i) + ".", L, seq, seq_pad, heads, hd, ln_eps, qk_norm, g1, g2, attn_cat, s);
+    if (r != BD_OK) return r;
   }
-  if (!e->aux_stream) {
-    CK(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-  }
-  const int d = e->d;
-  const int Lh[2] = {L / 2, L - L / 2};
-  CK(cudaEventRecord(e->ev_fork, s));
-  CK(cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
-  for (int h = 0; h < 2; ++h) {
-    cudaStream_t sh = h == 0 ? s : e->aux_stream;
-    const size_t l0 = h == 0 ? 0 : static_cast<size_t>(Lh[0]);
-    const size_t row0 = l0 * seq;
-    const size_t qk0 = l0 * heads * static_cast<size_t>(seq_pad) * hd * 2;   // bf16 Q / K / V^T: [L*heads, seq_pad, hd] elements
-    BlockBufs b{X + row0 * d, static_cast<char*>(e->H) + row0 * d * 2, static_cast<char*>(e->G) + row0 * 4 * d * 2,
-                static_cast<char*>(e->Q) + qk0, static_cast<char*>(e->K) + qk0, static_cast<char*>(e->V) + qk0,
-                static_cast<char*>(e->O) + row0 * d * 2};
-    for (int i = 0; i < layers; ++i) {
-      int r = run_block_bufs(e, b, prefix + std::to_string(i) + ".", Lh[h], seq, seq_pad, heads, hd, ln_eps, qk_norm, g1, g2, attn_cat, sh);
-      if (r != BD_OK) return r;
-    }
-  }
-  CK(cudaEventRecord(e->ev_join, e->aux_stream));
-  CK(cudaStreamWaitEvent(s, e->ev_join, 0));
   return BD_OK;
 }
 
@@ -796,7 +684,7 @@ extern "C" int bd_attention(const void* Q, const void* K, const void* V, void* O
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (precision == BD_PRECISION_BF16)
     CK(attention_tc(reinterpret_cast<const bf16*>(Q), reinterpret_cast<const bf16*>(K), reinterpret_cast<const bf16*>(V),
-                    reinterpret_cast<bf16*>(O), L, heads, head_dim, seq, seq_pad, scale, variant, s));
+                    reinterpret_cast<bf16*>(O), L, heads, head_dim, seq, seq_pad, scale, s));
   else
     CK(attention_f32(reinterpret_cast<const float*>(Q), reinterpret_cast<const float*>(K), reinterpret_cast<const float*>(V),
                      reinterpret_cast<float*>(O), L, heads, head_dim, seq, seq_pad, scale, s));

@@ -37,26 +37,19 @@ struct GemmEpi {
   float rms_eps = 1e-6f;
 };
 
-// --- tensor-core path (gemm_tc.cu / attn_tc.cu) ---
+// --- tensor-core path ---
+// CTA-pair tcgen05 GEMM (cta_group::2, 256 x BN tiles) with fused epilogues: gemm_tc2.cu
 cudaError_t gemm_tc(const bf16* A, const bf16* W, int M, int N, int K, int epi, const GemmEpi& e, cudaStream_t s);
-// same contract, CTA pairs (cta_group::2, 256 x BN tiles): gemm_tc2.cu.  gemm_tc() dispatches to it unless BD_GEMM_PAIR=0.
-cudaError_t gemm_tc_pair(const bf16* A, const bf16* W, int M, int N, int K, int epi, const GemmEpi& e, cudaStream_t s);
-// Q,K [BH, seq_pad, hd] bf16, Vt [BH, hd, seq_pad] bf16 -> O [L*seq, heads*hd] bf16 (token-major)
-// variant: 0 = P staged in shared memory (SS), 1 = P kept in tensor memory (TS), 2 = persistent ping-pong kernel (attn_tc2.cu)
+// Q,K [BH, seq_pad, hd] bf16, Vt [BH, hd, seq_pad] bf16 -> O [L*seq, heads*hd] bf16 (token-major): persistent kernel, two
+// query tiles per CTA in ping-pong, P in tensor memory (attn_tc2.cu)
 cudaError_t attention_tc(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int head_dim, int seq,
-                         int seq_pad, float scale, int variant, cudaStream_t s);
-// v2: persistent, two query tiles per CTA in ping-pong, P in tensor memory (attn_tc2.cu); variant 2 of attention_tc
-cudaError_t attention_tc2(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int head_dim, int seq,
-                          int seq_pad, float scale, cudaStream_t s);
+                         int seq_pad, float scale, cudaStream_t s);
 // launchers that enqueue more than one kernel report the extra ones here; the engine folds them into bd_launch_count()
 void note_extra_launches(int n);
 int take_extra_launches();
-void tc_set_num_sms(int n);
-// Traversal direction of the next launches (tiles / rows / work items walked last-to-first when set).  The engine
-// alternates it from kernel to kernel so that each kernel starts on the data its predecessor touched last, i.e. on what
-// is still resident in the 126 MB L2 (the activations of one layer are 150-600 MB).
-void tc_set_reverse(int r);
-int tc_reverse();
+// per-device plumbing (tc_host.cu): SM count of the current device; dynamic-shared-memory opt-in of a kernel on the current device
+int tc_num_sms();
+cudaError_t tc_ensure_smem(const void* kernel, int bytes);
 const char* tc_last_error();
 
 // --- SIMT fp32 path + memory-bound kernels (kernels_simt.cu) ---

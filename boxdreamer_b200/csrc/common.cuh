@@ -397,32 +397,6 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 // (fence_proxy_async_smem above: executed by every smem writer before the issuing thread's TMA store)
 
-// ------------------------------------------------------------------------------------------
-// Programmatic dependent launch (build with -DBD_PDL; off by default, not yet measured): the next kernel of the stream is
-// allowed to start while this one drains, runs its prologue (barrier init, TMEM allocation, descriptor prefetch) and then
-// blocks in pdl_wait() until the predecessor has completed and its writes are visible.
-#ifdef BD_PDL
-#include <utility>
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
-}
-#else
-__device__ __forceinline__ void pdl_wait() {}
-__device__ __forceinline__ void pdl_launch_dependents() {}
-#endif
 
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack_f32x2(float a, float b) {

@@ -30,7 +30,6 @@ struct GemmArgs {
   GemmEpi e;
   int qkv_col_base = 0;  // EPI_QKV on a column slice of the q|k|v weight: global column of this GEMM's column 0
   int m_fastest = 0;  // tile order: consecutive tiles walk M (swapped-operand V^T GEMM: the token block is shared)
-  int reverse = 0;    // walk the tiles last-to-first (L2 ping-pong between consecutive kernels, see tc_set_reverse)
 };
 
 __device__ __forceinline__ float gelu_erf_fast(float x) {

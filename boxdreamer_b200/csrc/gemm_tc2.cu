@@ -82,11 +82,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS);
     tmem_relinquish_2sm();
   }
-  pdl_launch_dependents();
   tc_fence_before();
   cluster_sync_all();   // barriers of BOTH CTAs are initialised before anyone signals across the pair
   tc_fence_after();
-  pdl_wait();           // (BD_PDL builds) no global access before this point
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
   if (warp == 0) {
@@ -94,7 +92,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = pair; tile < num_tiles; tile += npairs) {
-      const int tt = args.reverse ? num_tiles - 1 - tile : tile;
+      const int tt = tile;
       const int m_blk = args.m_fastest ? tt % tiles_m : tt / tiles_n;
       const int n_blk = args.m_fastest ? tt / tiles_m : tt % tiles_n;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -149,7 +147,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int tt = args.reverse ? num_tiles - 1 - tile : tile;
+      const int tt = tile;
       const int m_blk = args.m_fastest ? tt % tiles_m : tt / tiles_n;
       const int n_blk = args.m_fastest ? tt / tiles_m : tt % tiles_n;
       const int row_w = m_blk * 2 * BM + static_cast<int>(rank) * BM + quad * 32;
@@ -183,9 +181,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-static int g_num_sms2 = 0;
-extern thread_local std::string g_tc_err_2;
-thread_local std::string g_tc_err_2;
 
 template <int BN, int EPI, int HD, bool TMAOUT>
 static cudaError_t launch2(const bf16* A, const bf16* W, int M, int N, int K, const GemmEpi& e, cudaStream_t s, int col_base = 0) {
@@ -214,31 +209,17 @@ static cudaError_t launch2(const bf16* A, const bf16* W, int M, int N, int K, co
     if (!ok) return cudaErrorInvalidValue;
   }
   auto kern = gemm_tc2_kernel<BN, EPI, HD, TMAOUT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (err != cudaSuccess) return err;
-    attr_set = true;
-  }
-  if (g_num_sms2 == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms2, cudaDevAttrMultiProcessorCount, dev);
-  }
+  cudaError_t aerr = tc_ensure_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES);
+  if (aerr != cudaSuccess) return aerr;
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
-  const int max_pairs = g_num_sms2 / 2;
+  const int max_pairs = tc_num_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   GemmArgs args{M, N, K, e, col_base, m_fastest ? 1 : 0};
-  args.reverse = tc_reverse();
-#ifdef BD_PDL
-  return launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, tmA, tmB, tmOut, tmOut2, args);
-#else
   kern<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, tmOut, tmOut2, args);
   return cudaGetLastError();
-#endif
 }
 
-cudaError_t gemm_tc_pair(const bf16* A, const bf16* W, int M, int N, int K, int epi, const GemmEpi& e, cudaStream_t s) {
+cudaError_t gemm_tc(const bf16* A, const bf16* W, int M, int N, int K, int epi, const GemmEpi& e, cudaStream_t s) {
   if (M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0 || (N % 4) != 0) return cudaErrorInvalidValue;
   const char* tv = getenv("BD_GEMM_TMA_EPI");   // debug switch: 0 = register/LSU epilogue everywhere
   const bool tma_out = (N % 64) == 0 && !(tv && atoi(tv) == 0);

@@ -2,7 +2,7 @@
 // and the memory-bound glue kernels shared by both precision modes (LayerNorm, im2col, patchify,
 // token fusion, query gather, unpatchify + sigmoid).
 #include "bd_internal.h"
-#include "common.cuh"  // pdl_wait / pdl_launch_dependents (no-ops unless built with -DBD_PDL)
+#include "common.cuh"
 
 namespace bd {
 
@@ -225,11 +225,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ b, float eps, float* __restrict__ out_f32,
                                                            bf16* __restrict__ out_bf16, int rows_out, int rows_out_per,
-                                                           int rows_in_per, int row_off, int reverse) {
+                                                           int rows_in_per, int row_off) {
   constexpr int D = 768;
-  pdl_launch_dependents();
-  pdl_wait();
-  const int r = (reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows_out) return;
   long long rin = r;
@@ -277,13 +275,8 @@ __global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restri
 cudaError_t layernorm(const float* x, const float* w, const float* b, float eps, float* out_f32, bf16* out_bf16, int rows_out,
                       int d, int rows_out_per, int rows_in_per, int row_off, cudaStream_t s) {
   if (d == 768)
-#ifdef BD_PDL
-    return launch_pdl(layernorm768_kernel, dim3((rows_out + 7) / 8), dim3(256), 0, s, x, w, b, eps, out_f32, out_bf16, rows_out, rows_out_per,
-                      rows_in_per, row_off, tc_reverse());
-#else
     layernorm768_kernel<<<(rows_out + 7) / 8, 256, 0, s>>>(x, w, b, eps, out_f32, out_bf16, rows_out, rows_out_per, rows_in_per,
-                                                           row_off, tc_reverse());
-#endif
+                                                           row_off);
   else
     layernorm_kernel<<<(rows_out + 7) / 8, 256, 0, s>>>(x, w, b, eps, out_f32, out_bf16, rows_out, d, rows_out_per, rows_in_per,
                                                         row_off);

@@ -54,7 +54,7 @@ typedef struct {
   int32_t dino_registers;  /* 4                                                */
   int32_t dino_pretrain_grid; /* 37 (pos_embed is 1 + 37*37 rows)              */
   int32_t precision;       /* bd_precision                                     */
-  int32_t attn_variant;    /* 0: P through shared memory, 1: P through tensor memory, 2: persistent ping-pong kernel */
+  int32_t attn_variant;    /* reserved (one attention kernel is built: csrc/attn_tc2.cu); pass 2                  */
   int32_t max_batch;       /* B the workspace is sized for                     */
   int32_t max_views;       /* T (references + query)                           */
 } bd_config;
@@ -161,7 +161,7 @@ int bd_gemm(const void* A, const void* W, const float* bias, const float* gamma,
 int bd_qkv_project(const void* x, const void* W, const float* bias, const float* q_norm_w, const float* k_norm_w, void* Q,
                    void* K, void* V, void* scratch, int32_t L, int32_t seq, int32_t seq_pad, int32_t heads, int32_t head_dim,
                    int32_t precision, void* stream);
-/* O [L*seq, heads*hd] = softmax(scale * Q K^T) V on the layouts above */
+/* O [L*seq, heads*hd] = softmax(scale * Q K^T) V on the layouts above; `variant` is reserved (ignored) */
 int bd_attention(const void* Q, const void* K, const void* V, void* O, int32_t L, int32_t heads, int32_t head_dim, int32_t seq,
                  int32_t seq_pad, float scale, int32_t precision, int32_t variant, void* stream);
 int bd_layernorm(const float* x, const float* w, const float* b, float eps, float* out_f32, void* out_bf16, int32_t rows,

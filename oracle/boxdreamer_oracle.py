@@ -64,9 +64,9 @@ def dino_prepare_tokens(images: torch.Tensor, w: dict, patch: int = 14) -> torch
     images [L,3,S,S] in [0,1] -> tokens [L, 1+4+P, d]
     """
     L, _, S, _ = images.shape
-    mean = torch.tensor(_RESNET_MEAN).view(1, 3, 1, 1)
-    std = torch.tensor(_RESNET_STD).view(1, 3, 1, 1)
-    x = (images.float() - mean) / std
+    mean = torch.tensor(_RESNET_MEAN, device=images.device).view(1, 3, 1, 1)
+    std = torch.tensor(_RESNET_STD, device=images.device).view(1, 3, 1, 1)
+    x = (images - mean) / std   # bf16 - fp32 promotes to fp32 (dinov2.py:45-46)
     # patch_embed.py:65,75-78: conv k=14 s=14, flatten(2).transpose(1,2)
     x = F.conv2d(x, w["patch_embed.proj.weight"], w["patch_embed.proj.bias"], stride=patch)
     x = x.flatten(2).transpose(1, 2)
@@ -154,16 +154,18 @@ def unpatchify(x: torch.Tensor, p: int, c: int) -> torch.Tensor:
 
 
 def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
-    """blocks.py:44-56 LlamaRMSNorm."""
+    """blocks.py:44-56 LlamaRMSNorm: fp32 arithmetic, result cast back to the input dtype (bf16 under autocast)."""
     var = x.float().pow(2).mean(-1, keepdim=True)
-    return weight * (x.float() * torch.rsqrt(var + eps))
+    return (weight * (x.float() * torch.rsqrt(var + eps))).to(x.dtype)
 
 
-def decoder_block(x: torch.Tensor, w: dict, i: int, heads: int = 8) -> torch.Tensor:
+def decoder_block(x: torch.Tensor, w: dict, i: int, heads: int = 8, attention: str = "sdpa") -> torch.Tensor:
     """blocks.py:876-886 SelfAttentionBlock.forward + blocks.py:243-302 Attention.forward.
 
     LayerNorm eps is 1e-5 (get_layernorm passes the literal, blocks.py:805), MLP = timm Mlp with
-    exact-erf GELU (blocks.py:859-867).
+    exact-erf GELU (blocks.py:859-867).  `attention`: "sdpa" = F.scaled_dot_product_attention (blocks.py:273-285, the
+    branch taken when flash_attn is not importable, e.g. on CPU); "flash" = flash_attn_func on [B,N,H,hd]
+    (blocks.py:259-272, taken when flash_attn is importable and N > B; CUDA + half precision only).
     """
     p = f"decoder.attn.{i}."
     B, N, d = x.shape
@@ -174,8 +176,14 @@ def decoder_block(x: torch.Tensor, w: dict, i: int, heads: int = 8) -> torch.Ten
     q, k, v = qkv.unbind(0)
     q = rms_norm(q, w[p + "attn.q_norm.weight"])
     k = rms_norm(k, w[p + "attn.k_norm.weight"])
-    a = F.scaled_dot_product_attention(q, k, v, scale=hd ** -0.5)
-    a = a.transpose(1, 2).reshape(B, N, d)
+    if attention == "flash" and N > B:
+        from flash_attn import flash_attn_func
+        a = flash_attn_func(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3), dropout_p=0.0,
+                            softmax_scale=hd ** -0.5)
+        a = a.reshape(B, N, d)
+    else:
+        a = F.scaled_dot_product_attention(q, k, v, scale=hd ** -0.5)
+        a = a.transpose(1, 2).reshape(B, N, d)
     a = F.linear(a, w[p + "attn.proj.weight"], w[p + "attn.proj.bias"])
     x = x + a
     h = F.layer_norm(x.float(), (d,), w[p + "norm2.weight"], w[p + "norm2.bias"], 1e-5)
@@ -186,7 +194,7 @@ def decoder_block(x: torch.Tensor, w: dict, i: int, heads: int = 8) -> torch.Ten
 
 
 def betr_forward(bbox_feat: torch.Tensor, rgb_feat: torch.Tensor, query_idx: torch.Tensor, w: dict,
-                 num_layers: int = 12, patch: int = 14, seams: dict | None = None):
+                 num_layers: int = 12, patch: int = 14, seams: dict | None = None, attention: str = "sdpa"):
     """BETR.forward (betr.py:249-308) for pose_representation='bb8', bbox_representation='heatmap',
     use_pretrained=True.
 
@@ -196,31 +204,34 @@ def betr_forward(bbox_feat: torch.Tensor, rgb_feat: torch.Tensor, query_idx: tor
     P = rgb_feat.shape[2]
     d = rgb_feat.shape[3]
     # betr.py:310-331 _process_pretrained_features
-    r = rgb_feat.reshape(B * T, P, d).float()
+    dev = rgb_feat.device
+    r = rgb_feat.reshape(B * T, P, d)
     r = F.linear(r, w["decoder.input_transform.fc1.weight"], w["decoder.input_transform.fc1.bias"])
     r = F.gelu(r)  # vggsfm Mlp (modules.py:127-162), Dropout(0.1) inert in eval
     r = F.linear(r, w["decoder.input_transform.fc2.weight"], w["decoder.input_transform.fc2.bias"])
     r = F.layer_norm(r, (d,), None, None, 1e-6)  # betr.py:161 affine=False
     r = r.view(B, T, P, d)
-    pf = patchify(bbox_feat.reshape(B * T, C, S, S).float(), patch, C).view(B, T, P, patch * patch * C)
+    pf = patchify(bbox_feat.reshape(B * T, C, S, S), patch, C).view(B, T, P, patch * patch * C)
     pf = F.linear(pf, w["decoder.bbox_emb.weight"], w["decoder.bbox_emb.bias"])
     # betr.py:282-290: masked positions <- learnable query
-    mask = torch.zeros(B, T, dtype=torch.bool)
-    mask[torch.arange(B), query_idx] = True  # BoxDreamerModel.py:204-207
+    mask = torch.zeros(B, T, dtype=torch.bool, device=dev)
+    mask[torch.arange(B, device=dev), query_idx] = True  # BoxDreamerModel.py:204-207
     pf = pf.clone()
-    pf[mask] = w["decoder.bbox_learnable_query"].expand(B, P, d)
+    pf[mask] = w["decoder.bbox_learnable_query"].expand(B, P, d).to(pf.dtype)
     # betr.py:351-401 _generate_fused_features (use_pretrained branch)
     g = int(P ** 0.5)
-    fuse = pf + r + sincos_pos_embed_2d(d, g).view(1, 1, P, d)
+    fuse = pf + r + sincos_pos_embed_2d(d, g).view(1, 1, P, d).to(dev)
     x = fuse.reshape(B, T * P, d)
     if seams is not None:
         seams["fused"] = x
     for i in range(num_layers):
-        x = decoder_block(x, w, i)
+        x = decoder_block(x, w, i, attention=attention)
         if seams is not None and i in (0, 5, 11):
             seams[f"dec_block{i}"] = x
     x = x.view(B, T, P, d)
     q = x[mask]  # [B,P,d] (one True per row)
+    if seams is not None:
+        seams["query_tokens"] = q
     logits = F.linear(q, w["decoder.bbox_proj.weight"], w["decoder.bbox_proj.bias"])  # betr.py:419
     heat = unpatchify(logits, patch, C)
     query_ret = 2 * torch.sigmoid(heat) - 1  # betr.py:432-435
@@ -246,7 +257,7 @@ def corners_topk(query_ret: torch.Tensor, k: int = 20):
     xs = (idx % W).float().mean(dim=2)
     ys = (idx // W).float().mean(dim=2)
     kp = torch.stack([xs, ys], dim=2)
-    norm = kp / torch.tensor([W, H], dtype=torch.float32).view(1, 1, 2) * 2 - 1
+    norm = kp / torch.tensor([W, H], dtype=torch.float32, device=kp.device).view(1, 1, 2) * 2 - 1
     return idx, kp, norm
 
 
@@ -373,25 +384,53 @@ def recover_pose_from_bb8(keypoints_px: torch.Tensor, bbox_3d: torch.Tensor, K: 
     return poses
 
 
+def recover_pose_from_bb8_cv2(keypoints_px: torch.Tensor, bbox_3d: torch.Tensor, K: torch.Tensor) -> torch.Tensor:
+    """box_utils.py:139-197 as the reference executes it: a Python loop over the samples with three device->host copies
+    each, `cv2.solvePnPRansac` (result discarded, box_utils.py:168-169), `cv2.solvePnP(ITERATIVE)`, `cv2.Rodrigues`, and a
+    host->device copy of every pose.  Needs OpenCV (third-party, un-vendored); used by bench.py's reference-on-GPU leg and by
+    the fixtures' generator, never by the product."""
+    import cv2
+    B = keypoints_px.shape[0]
+    bbox_3d, K = bbox_3d.float(), K.float()
+    poses = torch.zeros(B, 4, 4, device=keypoints_px.device)
+    for b in range(B):
+        pts_2d = keypoints_px[b].cpu().numpy().astype(np.float32)
+        pts_3d = bbox_3d[b].cpu().numpy().astype(np.float32)
+        K_np = K[b].cpu().numpy().astype(np.float32)
+        try:
+            cv2.solvePnPRansac(pts_3d, pts_2d, K_np, None, reprojectionError=1.0, confidence=0.99, flags=cv2.SOLVEPNP_ITERATIVE)
+            ok, rvec, tvec = cv2.solvePnP(pts_3d, pts_2d, K_np, None, flags=cv2.SOLVEPNP_ITERATIVE)
+            if ok:
+                R, _ = cv2.Rodrigues(rvec)
+                pose = np.hstack((R.astype(np.float32), tvec.reshape(3, 1).astype(np.float32)))
+                poses[b, :3, :] = torch.from_numpy(pose).to(keypoints_px.device)
+                poses[b, 3, 3] = 1.0
+        except Exception:
+            continue
+    return poses
+
+
 # ----------------------------------------------------------------------------------------------
 # full forward
 
 
 def forward(data: dict, dec_w: dict, dino_w: dict, num_layers: int = 12, dino_depth: int = 12,
-            with_pnp: bool = True, seams: dict | None = None) -> dict:
+            with_pnp: bool = True, seams: dict | None = None, attention: str = "sdpa", pnp: str = "numpy") -> dict:
     """BoxDreamer.forward (BoxDreamerModel.py:112-191), eval mode.  Does not mutate `data`;
-    returns the keys the reference writes plus the fp32 seams."""
+    returns the keys the reference writes plus the fp32 seams.  Runs on whatever device `data` and the weights live on
+    (CPU fp32 = the parity oracle; CUDA under torch.autocast(bf16) = the reference's production flow, used as the same-box
+    baseline).  `attention`: see decoder_block; `pnp`: "numpy" = the pinned restatement, "cv2" = the reference's host loop."""
     images = data["images"]
     B, T, _, S, _ = images.shape
     qidx = data["query_idx"]
-    mask = torch.zeros(B, T, dtype=torch.bool)
-    mask[torch.arange(B), qidx] = True
+    mask = torch.zeros(B, T, dtype=torch.bool, device=images.device)
+    mask[torch.arange(B, device=images.device), qidx] = True
     feats = dino_forward(images.reshape(B * T, 3, S, S), dino_w, dino_depth, seams=seams)
     P = feats.shape[1]
     feats = feats.view(B, T, P, -1)
     if seams is not None:
         seams["dino_feats"] = feats
-    logits, query_ret = betr_forward(data["bbox_feat"], feats, qidx, dec_w, num_layers, seams=seams)
+    logits, query_ret = betr_forward(data["bbox_feat"], feats, qidx, dec_w, num_layers, seams=seams, attention=attention)
     idx, kp, norm = corners_topk(query_ret)
     out = {"camera_mask": mask, "logits": logits, "query_ret": query_ret, "topk_idx": idx,
            "keypoints_px": kp, "keypoints_norm": norm}
@@ -405,7 +444,10 @@ def forward(data: dict, dec_w: dict, dino_w: dict, num_layers: int = 12, dino_de
     out["regression_boxes"] = reg
     pred_poses = data["poses"].clone()
     if with_pnp:
-        qp = recover_pose_from_bb8(kp, data["bbox_3d"][mask], data["non_ndc_intrinsics"][mask])
+        if pnp == "cv2":
+            qp = recover_pose_from_bb8_cv2(kp, data["bbox_3d"][mask], data["non_ndc_intrinsics"][mask])
+        else:
+            qp = recover_pose_from_bb8(kp.cpu(), data["bbox_3d"][mask].cpu(), data["non_ndc_intrinsics"][mask].cpu()).to(kp.device)
         out["query_poses"] = qp
         pred_poses[mask] = qp.to(pred_poses.dtype)
     out["pred_poses"] = torch.nan_to_num(pred_poses, nan=0.0, posinf=0.0, neginf=0.0)

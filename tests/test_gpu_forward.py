@@ -114,9 +114,10 @@ def test_exact_path_matches_oracle_full_tensors(weights):
 
 
 def test_bf16_tensor_path_statistical_agreement(weights):
-    """bf16 tcgen05 path vs the fp32 oracle.  Stated tolerance: logits mean|d| <= 2e-2 * max|ref| and
-    max|d| <= 1e-1 * max|ref| after 24 transformer layers in bf16 (the reference's own autocast probe shows
-    heat-map |d| max 0.023 / mean 0.0036); >= 90 % of corners within 2 px."""
+    """bf16 tcgen05 path vs the fp32 oracle at a small ragged shape.  Stated tolerance: logits mean|d| <= 2.5e-3 * max|ref| and
+    max|d| <= 1.5e-2 * max|ref| after 24 transformer layers in bf16 -- about twice the values measured on B200 (1.0e-3 /
+    5.9e-3).  With these random-init weights the maps are noise, so corner agreement is only printed here; corners and poses of
+    the bf16 path are gated on well-conditioned maps in tests/test_gpu_bf16_parity.py (config-2 shape)."""
     from oracle import boxdreamer_oracle as O
     dec, dino = weights
     B, T = 2, 3
@@ -133,8 +134,8 @@ def test_bf16_tensor_path_statistical_agreement(weights):
     scale = ref_l.abs().max().item()
     print(f"bf16 logits: max|d|/max|ref| = {diff.max().item() / scale:.3e}, mean|d|/max|ref| = {diff.mean().item() / scale:.3e}")
     assert not torch.isnan(logits).any()
-    assert diff.mean().item() <= 2e-2 * scale
-    assert diff.max().item() <= 1e-1 * scale
+    assert diff.mean().item() <= 2.5e-3 * scale
+    assert diff.max().item() <= 1.5e-2 * scale
     px, nm = eng.corners_topk(heat)
     dist = (px.cpu() - ref["keypoints_px"]).norm(dim=-1)
     print(f"bf16 corners: median dist {dist.median().item():.3f} px, frac<2px {float((dist < 2).float().mean()):.3f}")
@@ -179,7 +180,7 @@ def test_336px_long_sequence_config(weights):
     data = synth.synth_inputs(B, T, S, seed=91)
     with torch.no_grad():
         ref = O.forward(data, dec, dino, with_pnp=False)
-    for precision, dtype, tol_max in (("exact", torch.float32, 1e-4), ("bf16", torch.bfloat16, 1e-1)):
+    for precision, dtype, tol_max in (("exact", torch.float32, 1e-4), ("bf16", torch.bfloat16, 2e-2)):
         m = BoxDreamer(make_config(S), precision=precision)
         m.load_state_dict(dec, strict=True)
         m.rgb_encoder.model.load_state_dict(dino, strict=True)

@@ -20,17 +20,10 @@ def _operands(M, N, K, seed):
     return A.cuda(), W.cuda(), b.cuda(), ref
 
 
-@pytest.fixture(params=[0, 1], ids=["cta1", "pair"])
-def gemm_pair(request):
-    """Runs the test once with the single-CTA GEMM and once with the CTA-pair (cta_group::2) GEMM."""
-    import os
-    old = os.environ.get("BD_GEMM_PAIR")
-    os.environ["BD_GEMM_PAIR"] = str(request.param)
-    yield request.param
-    if old is None:
-        os.environ.pop("BD_GEMM_PAIR", None)
-    else:
-        os.environ["BD_GEMM_PAIR"] = old
+@pytest.fixture
+def gemm_pair():
+    """(kept as a fixture name: every GEMM runs through the CTA-pair cta_group::2 kernel, gemm_tc2.cu)"""
+    return 1
 
 
 @pytest.mark.parametrize("M,N,K", [
@@ -107,16 +100,6 @@ def test_qkv_project_tc(lib, gemm_pair, L, seq, heads, hd, norm):
 
 
 ATT_CASES = [(1, 128, 8, 96), (2, 512, 8, 96), (3, 261, 12, 64), (1, 1536, 8, 96), (2, 700, 8, 96)]
-
-
-@pytest.mark.parametrize("L,seq,heads,hd", ATT_CASES)
-def test_attention_tc_p_in_smem(lib, L, seq, heads, hd):
-    _attention_case(lib, 0, L, seq, heads, hd)
-
-
-@pytest.mark.parametrize("L,seq,heads,hd", ATT_CASES)
-def test_attention_tc_p_in_tmem(lib, L, seq, heads, hd):
-    _attention_case(lib, 1, L, seq, heads, hd)
 
 
 @pytest.mark.parametrize("L,seq,heads,hd", ATT_CASES + [(5, 261, 12, 64), (3, 100, 8, 96), (1, 2000, 8, 96), (40, 261, 12, 64)])

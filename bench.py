@@ -174,8 +174,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"batch={B_PER_GPU} queries x {T_VIEWS - 1} refs, {IMG}px (configs[1]); each step = a {q}-query sample",
-                   "sample_queries_per_step": q, "views": T_VIEWS},
+        "config": {"workload": f"CPU ARM, BOUNDED SAMPLE: each step = {q} queries x {T_VIEWS - 1} refs, {IMG}px, fp32 (same per-query work as "
+                               f"configs[1], whose batch is {B_PER_GPU}; not the same batch size)",
+                   "sample_queries_per_step": q, "views": T_VIEWS, "same_config_as_ours": False},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{q} queries/step x {args.steps} steps, torch fp32 CPU restatement of BoxDreamer.forward (oracle/), numpy PnP"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -192,10 +193,11 @@ def cpu_baseline_sample():
     """Bounded CPU sample on rank 0 (N=1 only): the oracle port on all host cores."""
     from boxdreamer_b200 import synth
     from oracle import boxdreamer_oracle as O
+    from oracle import peaked_head
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     dec, dino = synth.synth_decoder_state_dict(0), synth.synth_dino_state_dict(0)
-    data = synth.synth_inputs(2, T_VIEWS, IMG, seed=1235)
+    data = peaked_head.inputs_with_visible_corners(2, T_VIEWS, IMG, seed=5000)
     with torch.no_grad():
         O.forward(synth.synth_inputs(1, T_VIEWS, IMG, seed=1), dec, dino)  # warm-up
         n, t0 = 0, time.perf_counter()
@@ -209,55 +211,135 @@ def cpu_baseline_sample():
             "sample": f"{n} queries (B=2 x T={T_VIEWS} per call) in {dt:.1f} s, torch fp32 CPU restatement (oracle/) + numpy PnP"}
     # the oracle's output on this sample doubles as the checker for the metric's second half ("pose ADD err vs ref")
     try:
-        with torch.no_grad():
-            ref = O.forward(data, dec, dino)
-        base["_parity"] = parity_vs_oracle(data, ref, dec, dino)
+        base["_parity"] = parity_vs_oracle(data, dec, dino)
     except Exception as exc:  # the parity note must never take the measurement down
         base["_parity"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
     return base
 
 
-def pose_add_error(P_a, P_b, bbox3d):
-    """ADD-style distance between two poses [4,4]: mean |(R_a x + t_a) - (R_b x + t_b)| over the 8 box corners and a
-    1000-point sample of the box volume.  numpy float64."""
-    import numpy as np
-    lo, hi = bbox3d.min(axis=0), bbox3d.max(axis=0)
-    rng = np.random.Generator(np.random.PCG64(7))
-    pts = np.concatenate([bbox3d, lo + (hi - lo) * rng.uniform(size=(1000, 3))])
-    a = pts @ P_a[:3, :3].T + P_a[:3, 3]
-    b = pts @ P_b[:3, :3].T + P_b[:3, 3]
-    return float(np.linalg.norm(a - b, axis=1).mean())
-
-
-def parity_vs_oracle(data, ref, dec, dino):
-    """The exact-precision GPU path on the cpu_baseline sample against the oracle's output for it: heat-map error, corner
-    equality, rotation / translation / ADD error of the recovered pose.  (The oracle is the checker here, not the thing
-    measured.)"""
+def parity_vs_oracle(data, dec, dino):
+    """The metric's second half ("pose ADD err vs ref") on the cpu_baseline sample, for BOTH precisions of the GPU path:
+    `exact` (fp32 kernels, the 1e-4 / bit-exact gate) and `bf16` (the path the throughput is measured on).  (a) Random-init
+    weights: heat-map logits against the oracle.  (b) The same weights with the head fitted so that the maps are peaked at the
+    ground-truth corners (oracle/peaked_head.py) -- corners, rotation, translation and ADD against the oracle's pose and
+    against the ground-truth pose.  The oracle is the checker here, not the thing measured."""
     import numpy as np
     from boxdreamer_b200 import BoxDreamer
     from boxdreamer_b200.config import make_config
-    m = BoxDreamer(make_config(IMG), precision="exact")
-    m.load_state_dict(dec, strict=True)
-    m.rgb_encoder.model.load_state_dict(dino, strict=True)
-    m = m.cuda().eval()
-    out = m({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in data.items()})
-    torch.cuda.synchronize()
+    from oracle import boxdreamer_oracle as O
+    from oracle import peaked_head as PH
+    B, T = data["images"].shape[:2]
+    with torch.no_grad():
+        ref = O.forward(data, dec, dino, with_pnp=False)
+    dec2, refp = PH.oracle_with_peaked_head(data, dec, dino)
     mask = ref["camera_mask"]
-    scale = float(ref["pred_bbox"].abs().max())
-    heat_err = float((out["pred_bbox"].cpu() - ref["pred_bbox"]).abs().max()) / scale
-    corners_equal = bool(torch.allclose(out["regression_boxes"].cpu(), ref["regression_boxes"], atol=1e-6, rtol=0))
-    Pg = out["pred_poses"].cpu()[mask].double().numpy()
-    Po = ref["pred_poses"][mask].double().numpy()
     X = data["bbox_3d"][mask].double().numpy()
-    rot = [float(np.degrees(2.0 * np.arcsin(min(np.linalg.norm(Pg[b, :3, :3] - Po[b, :3, :3]) / (2.0 * np.sqrt(2.0)), 1.0)))) for b in range(len(Pg))]
-    tr = [float(np.linalg.norm(Pg[b, :3, 3] - Po[b, :3, 3])) for b in range(len(Pg))]
-    add = [pose_add_error(Pg[b], Po[b], X[b]) for b in range(len(Pg))]
-    del m
-    torch.cuda.empty_cache()
-    return {"precision": "exact (fp32 kernels; the bf16 throughput path is compared statistically in tests/)",
-            "queries": int(len(Pg)), "heat_max_err_rel": heat_err, "corners_equal": corners_equal,
-            "rot_err_deg_max": max(rot), "trans_err_max": max(tr), "add_err_max": max(add),
-            "tolerance": "heat 1e-4 rel, corners bit-exact (1e-6), R|t 1e-3 deg / 1e-4 rel"}
+    diam = [float(np.linalg.norm(X[b].max(0) - X[b].min(0))) for b in range(B)]
+    Po, Pgt = refp["query_poses"].double().numpy(), refp["gt_poses"].double().numpy()
+    out = {"queries": int(B), "sample": "the cpu_baseline sample (B=2, T=6, 224 px), ground-truth corners inside the crop",
+           "tolerance": "exact: logits 1e-4 rel, corners bit-exact, R|t 1e-3 deg / 1e-4 rel; bf16: logits mean 2.5e-3 / max 1.5e-2 of max|ref|, "
+                        "corners 0.5 px, rotation 0.5 deg, ADD 0.5 % of the box diameter (tests/test_gpu_bf16_parity.py)",
+           "oracle_vs_ground_truth": {"rot_err_deg_max": max(PH.rot_err_deg(Po[b, :3, :3], Pgt[b, :3, :3]) for b in range(B)),
+                                      "add_over_diameter_max": max(PH.add_err(Po[b], Pgt[b], X[b]) / diam[b] for b in range(B))}}
+    K_q = data["non_ndc_intrinsics"][mask].float().cuda().contiguous()
+    X_q = data["bbox_3d"][mask].float().cuda().contiguous()
+    for precision, dtype in (("exact", torch.float32), ("bf16", torch.bfloat16)):
+        res = {}
+        for tag, weights in (("random_init", dec), ("fitted_head", dec2)):
+            m = BoxDreamer(make_config(IMG), precision=precision)
+            m.load_state_dict(weights, strict=True)
+            m.rgb_encoder.model.load_state_dict(dino, strict=True)
+            m = m.cuda().eval()
+            d = {k: ((v.to(dtype) if v.is_floating_point() else v).cuda() if torch.is_tensor(v) else v) for k, v in data.items()}
+            eng = m._engine_for(d["images"], B, T)
+            if tag == "random_init":
+                feats = eng.dino_forward(d["images"].view(B * T, 3, IMG, IMG).contiguous())
+                _, logits = eng.decoder_forward(d["bbox_feat"].contiguous(), feats, d["query_idx"], want_logits=True)
+                diff = (logits.view(B, -1, 1568).cpu() - ref["logits"]).abs()
+                scale = float(ref["logits"].abs().max())
+                res["logits_mean_err_rel"] = float(diff.mean()) / scale
+                res["logits_max_err_rel"] = float(diff.max()) / scale
+            else:
+                _, px, _, poses = eng.forward(d["images"].contiguous(), d["bbox_feat"].contiguous(), d["query_idx"], X_q, K_q)
+                torch.cuda.synchronize()
+                Pg = poses.double().cpu().numpy()
+                res["corner_err_px_max"] = float((px.cpu() - refp["keypoints_px"]).norm(dim=-1).max())
+                res["rot_err_deg_max"] = max(PH.rot_err_deg(Pg[b, :3, :3], Po[b, :3, :3]) for b in range(B))
+                res["trans_err_max"] = max(float(np.linalg.norm(Pg[b, :3, 3] - Po[b, :3, 3])) for b in range(B))
+                res["add_over_diameter_max"] = max(PH.add_err(Pg[b], Po[b], X[b]) / diam[b] for b in range(B))
+                res["vs_ground_truth"] = {"rot_err_deg_max": max(PH.rot_err_deg(Pg[b, :3, :3], Pgt[b, :3, :3]) for b in range(B)),
+                                          "add_over_diameter_max": max(PH.add_err(Pg[b], Pgt[b], X[b]) / diam[b] for b in range(B))}
+            del m, eng
+            torch.cuda.empty_cache()
+        out[precision] = res
+    return out
+
+
+def reference_gpu_leg(dec, dino, data, dev, steps=3):
+    """The bar on the same box: the reference's production flow -- the oracle's functional
+    restatement of BoxDreamer.forward on CUDA under torch.autocast(bf16), attention through flash_attn_func when importable
+    (blocks.py:259-272) and through F.scaled_dot_product_attention (blocks.py:273-285), followed by the reference's host loop of
+    cv2.solvePnPRansac (discarded) + cv2.solvePnP(ITERATIVE) (box_utils.py:139-197, one host thread).  Inputs resident on the
+    device, same weights and inputs as our arm.  Reported beside our number; not the driver's --impl reference arm."""
+    from oracle import boxdreamer_oracle as O
+    out = {"cores_used": 1, "host_cores": os.cpu_count(), "dtype": "bf16 autocast", "queries_per_step": int(data["images"].shape[0])}
+    try:
+        import cv2
+        cv2.setNumThreads(0)   # run.py:21
+        out["cv2"] = cv2.__version__
+    except Exception as exc:
+        return {"unavailable": f"cv2: {exc}"[:120]}
+    dec_c = {k: v.to(dev) for k, v in dec.items()}
+    dino_c = {k: v.to(dev) for k, v in dino.items()}
+    d = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()}
+    B, T = d["images"].shape[:2]
+    modes = ["sdpa"]
+    try:
+        import flash_attn
+        modes.insert(0, "flash")
+        out["flash_attn"] = getattr(flash_attn, "__version__", "?")
+    except Exception:
+        out["flash_attn"] = None
+    mask = torch.zeros(B, T, dtype=torch.bool, device=dev)
+    mask[torch.arange(B, device=dev), d["query_idx"]] = True
+    for mode in modes:
+        try:
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                O.forward(d, dec_c, dino_c, attention=mode, pnp="cv2")   # warm-up
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    O.forward(d, dec_c, dino_c, attention=mode, pnp="cv2")
+                torch.cuda.synchronize()
+                total = (time.perf_counter() - t0) / steps
+                # split: encoder / decoder / top-20 on the device (CUDA events), PnP loop on the host (wall clock)
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                ev[0].record()
+                feats = O.dino_forward(d["images"].reshape(B * T, 3, IMG, IMG), dino_c)
+                ev[1].record()
+                logits, query_ret = O.betr_forward(d["bbox_feat"], feats.view(B, T, feats.shape[1], -1), d["query_idx"], dec_c, attention=mode)
+                ev[2].record()
+                idx, kp, norm = O.corners_topk(query_ret)
+                ev[3].record()
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                O.recover_pose_from_bb8_cv2(kp, d["bbox_3d"][mask], d["non_ndc_intrinsics"][mask])
+                pnp_s = time.perf_counter() - t1
+            out[mode] = {"queries_per_s": B / total, "ms_per_step": total * 1e3,
+                         "split_ms": {"dino": ev[0].elapsed_time(ev[1]), "betr": ev[1].elapsed_time(ev[2]), "top20": ev[2].elapsed_time(ev[3]),
+                                      "pnp_host_loop": pnp_s * 1e3}}
+        except Exception as exc:
+            out[mode] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+    # the cv2 loop on clean corners (what a trained model produces): random-init heat maps are noise, on which solvePnPRansac
+    # runs its full iteration budget
+    try:
+        gt = (d["bbox_proj_crop"].float()[mask] + 1) / 2 * IMG
+        t1 = time.perf_counter()
+        O.recover_pose_from_bb8_cv2(gt, d["bbox_3d"][mask], d["non_ndc_intrinsics"][mask])
+        out["pnp_host_loop_ms_on_ground_truth_corners"] = (time.perf_counter() - t1) * 1e3
+    except Exception:
+        pass
+    return out
 
 
 def run_ours(args, rank, world, local_rank):
@@ -419,8 +501,76 @@ def run_ours(args, rank, world, local_rank):
                   "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in (h_images, h_px, h_qidx, h_K, h_X)),
                   "d2h_bytes_per_step": d2h, "api": "bd_forward_host_px (projected corners in, heat maps rasterised on the device)"}
 
-    cpu_base, parity = None, None
+    # ---- batch-1 latency (the only number the reference publishes: "over 40 FPS", 5 references, README.md:371, RTX 4090) ----
+    latency = None
+    if not args.quick and rank == 0:
+        d1 = {k: (v[:1].contiguous().to(dev) if torch.is_tensor(v) else v) for k, v in data.items()}
+        i1, b1, q1 = d1["images"], d1["bbox_feat"], d1["query_idx"]
+        X1, K1 = d_X[:1].contiguous(), d_K[:1].contiguous()
+        for _ in range(5):
+            eng.forward(i1, b1, q1, X1, K1, want_heat=False)
+        torch.cuda.synchronize()
+        lat = []
+        for _ in range(30):
+            t0 = time.perf_counter()
+            _, _, _, p1 = eng.forward(i1, b1, q1, X1, K1, want_heat=False)
+            p1.cpu()                                     # the caller reads the pose: device -> host inside the measurement
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat.sort()
+        with torch.no_grad():
+            for _ in range(3):
+                model(dict(d1))
+            torch.cuda.synchronize()
+            lat_m = []
+            for _ in range(20):
+                t0 = time.perf_counter()
+                out1 = model(dict(d1))
+                out1["pred_poses"].cpu()
+                lat_m.append((time.perf_counter() - t0) * 1e3)
+        lat_m.sort()
+        latency = {"config": "1 query x 5 reference views, 224 px, bf16, full forward incl. encoder of all 6 views + pose read-back",
+                   "engine_ms_median": lat[len(lat) // 2], "engine_ms_p90": lat[int(len(lat) * 0.9)], "engine_fps": 1e3 / lat[len(lat) // 2],
+                   "module_api_ms_median": lat_m[len(lat_m) // 2], "module_api_fps": 1e3 / lat_m[len(lat_m) // 2],
+                   "reference_published": "over 40 FPS on 1x RTX 4090 (README.md:371); not a B200 number"}
+
+    # ---- the module API (BoxDreamer.forward(data) -> data, the call the Lightning loop makes; device inputs) ----
+    module_api = None
+    if not args.quick:
+        dd = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()}
+        res_m = {}
+        for tag, full in (("reference_contract_pred_bbox_clone", True), ("lazy_pred_bbox", False)):
+            model.write_pred_bbox = full
+            with torch.no_grad():
+                for _ in range(2):
+                    model(dict(dd))
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n_m = max(2, min(args.steps, 10))
+                e0.record()
+                for _ in range(n_m):
+                    model(dict(dd))
+                e1.record()
+                barrier()
+            tm = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            res_m[tag] = world * B * n_m / (float(tm.item()) / 1e3)
+        model.write_pred_bbox = True
+        module_api = {"unit": UNIT, "api": "BoxDreamer.forward(data) -> data (device tensors in the dict, same keys as the reference)",
+                      "queries_per_s": res_m["reference_contract_pred_bbox_clone"],
+                      "queries_per_s_lazy_pred_bbox": res_m["lazy_pred_bbox"],
+                      "note": "reference contract = data['pred_bbox'] is a full [B,T,8,S,S] clone of bbox_feat with the query rows replaced "
+                              "(BoxDreamerModel.py:341-344, 308 MB at B=64 bf16); lazy = model.write_pred_bbox=False returns the query heat maps "
+                              "as data['pred_bbox_query'] [B,8,S,S] only"}
+        del dd
+
+    cpu_base, parity, ref_gpu = None, None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
+        try:
+            ref_gpu = reference_gpu_leg({k: v.cpu() for k, v in dec.items()}, {k: v.cpu() for k, v in dino.items()}, data, dev)
+        except Exception as exc:
+            ref_gpu = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+        torch.cuda.empty_cache()
         cpu_base = cpu_baseline_sample()
         parity = cpu_base.pop("_parity", None)
 
@@ -432,11 +582,14 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": f"batch={B} queries x {T - 1} reference views per GPU, {S}px, bf16 (BASELINE configs[1]; configs[2] at 8 GPUs)",
                        "global_batch": world * B, "views": T, "img_size": S, "weights": "random-init (synth seed 0)",
                        "l2": "inputs (424 MB/step) exceed L2; no flush needed", "parallelism": f"query-shard x{world}",
-                       "attn_variant": int(eng.cfg.attn_variant)},
+                       },
             "roofline": roofline, "roofline_gemm": roofline_gemm, "roofline_dino_attention": roofline_dino_attention,
             "roofline_e2e": roofline_e2e,
             "cpu_baseline": cpu_base,
             "pose_err_vs_reference": parity,
+            "reference_gpu_same_box": ref_gpu,
+            "latency_batch1": latency,
+            "e2e_module_api": module_api,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "bd_forward_host (C ABI, pinned host buffers)", "steps": e2e_steps},
             "e2e_device_rasterised_inputs": e2e_px,
@@ -444,6 +597,184 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks, "flops_per_query": fl["total"],
         }
         print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_config4(args, rank, world, local_rank):
+    """BASELINE configs[3]: batch = 256 queries x 16 reference views, 336 px (N = 17 * 576 = 9792 decoder tokens per query,
+    7144 GFLOP/query, attention 49 %).  The batch runs as micro-batches of `--micro-batch` queries through one workspace; the
+    micro-batch's synthetic inputs are generated once and reused by every micro-batch of the step (the values do not change
+    the work)."""
+    import ctypes as C
+    import torch.distributed as dist
+    from boxdreamer_b200 import BoxDreamer, _lib, synth
+    from boxdreamer_b200.config import make_config
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    Bq, T, S, mb = 256, 17, 336, args.micro_batch
+    peaks = load_peaks()
+    model = BoxDreamer(make_config(S), precision="bf16")
+    model.load_state_dict(synth.synth_decoder_state_dict(0), strict=True)
+    model.rgb_encoder.model.load_state_dict(synth.synth_dino_state_dict(0), strict=True)
+    model = model.to(dev).eval()
+    d = synth.synth_inputs(mb, T, S, seed=1237 + rank, dtype=torch.bfloat16)
+    mask = torch.zeros(mb, T, dtype=torch.bool)
+    mask[torch.arange(mb), d["query_idx"]] = True
+    img, bbox, qi = d["images"].to(dev).contiguous(), d["bbox_feat"].to(dev).contiguous(), d["query_idx"].to(dev)
+    X, K = d["bbox_3d"][mask].float().to(dev).contiguous(), d["non_ndc_intrinsics"][mask].float().to(dev).contiguous()
+    eng = model._engine_for(img, mb, T)
+    n_mb = Bq // mb
+
+    def step():
+        for _ in range(n_mb):
+            eng.forward(img, bbox, qi, X, K, want_heat=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3) if args.steps > 2 else 1):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = eng.lib.bd_launch_count(eng.handle)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = eng.lib.bd_launch_count(eng.handle) - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * Bq * args.steps / (ms / 1e3)
+    # in-step timing of the attention kernel (one micro-batch)
+    ncat = len(_lib.PROF_CATS)
+    ms_arr, n_arr = (C.c_double * ncat)(), (C.c_int64 * ncat)()
+    _lib.check(eng.lib.bd_profile_enable(eng.handle, 1))
+    _lib.check(eng.lib.bd_profile_read(eng.handle, ms_arr, n_arr, 1))
+    eng.forward(img, bbox, qi, X, K, want_heat=False)
+    _lib.check(eng.lib.bd_profile_read(eng.handle, ms_arr, n_arr, 1))
+    _lib.check(eng.lib.bd_profile_enable(eng.handle, 0))
+    kernel_ms = {name: ms_arr[i] for i, name in enumerate(_lib.PROF_CATS)}
+    fl = flops_per_query(T=T, P=576, n_tok=581)
+    N = T * 576
+    att_flops = mb * 4.0 * N * N * 768
+    att_ms = kernel_ms["attention"] / max(int(n_arr[_lib.PROF_CATS.index("attention")]), 1)
+    peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+    ach = att_flops / (att_ms / 1e3) / 1e12 if att_ms > 0 else 0.0
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"batch={Bq} queries x {T - 1} reference views per GPU, {S}px, bf16 (BASELINE configs[3], long-sequence stress), "
+                                   f"run as {n_mb} micro-batches of {mb}", "micro_batch": mb, "views": T, "img_size": S, "decoder_tokens": N,
+                       "l2": "activations of one micro-batch (>= 1 GB) exceed L2", "parallelism": f"query-shard x{world}"},
+            "roofline": {"bound": "tensor", "kernel": f"attn_tc2_kernel<96> (N = {N}, {mb} queries x 8 heads per launch)", "achieved": ach, "peak": peak,
+                         "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": None, "flops_per_launch": att_flops, "ms_per_launch": att_ms},
+            "roofline_e2e": {"achieved": fl["total"] * value / world / 1e12, "peak": peak, "unit": "TFLOP/s",
+                             "frac": fl["total"] * value / world / 1e12 / peak if peak else None},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "kernel_ms_per_micro_batch": kernel_ms, "clocks": clocks,
+            "flops_per_query": fl["total"]}), flush=True)
+    return 0
+
+
+def run_config5(args, rank, world, local_rank):
+    """BASELINE configs[4]: PnP kernel in isolation, 100 000 queries x 512 hypotheses, corner noise sigma in {0, 2, 5} px.
+    value = hypotheses/s of the robust mode (bd_pnp mode 1) at sigma = 2 px; per sigma: both modes, accuracy against the
+    ground truth, and the reference's cv2 calls on a sample (one host core, as the reference runs them)."""
+    import ctypes as C
+    import numpy as np
+    from boxdreamer_b200 import _lib, synth
+    if rank != 0:
+        return 0
+    torch.cuda.set_device(local_rank)
+    lib = _lib.load()
+    N, NH = args.pnp_queries, 512
+
+    def rot_err(Ra, Rb):
+        sgl = np.minimum(np.linalg.norm(Ra - Rb, axis=(-2, -1)) / (2 * np.sqrt(2)), 1.0)
+        return np.degrees(2 * np.arcsin(sgl))
+
+    def solve(c2, X3, Ks, opts, iters):
+        poses = torch.empty(c2.shape[0], 4, 4, device="cuda")
+        o = C.byref(opts) if opts is not None else None
+        for _ in range(max(args.warmup, 3) if opts is None else 1):
+            _lib.check(lib.bd_pnp(None, _lib.ptr(c2), _lib.ptr(X3), _lib.ptr(Ks), _lib.ptr(poses), o, c2.shape[0], 8, None))
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            _lib.check(lib.bd_pnp(None, _lib.ptr(c2), _lib.ptr(X3), _lib.ptr(Ks), _lib.ptr(poses), o, c2.shape[0], 8, None))
+        b.record()
+        torch.cuda.synchronize()
+        return poses.cpu().numpy().astype(np.float64), a.elapsed_time(b) / iters
+
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+    except Exception:
+        cv2 = None
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    per_sigma, headline = {}, None
+    for sigma in (0.0, 2.0, 5.0):
+        c2s, X3s, Kss, gts = synth.synth_pnp_cases(4096, sigma, seed=4321 + int(sigma))
+        rep = (N + 4095) // 4096
+        c2 = np.tile(c2s, (rep, 1, 1))[:N].copy()
+        X3, Ks, gt = np.tile(X3s, (rep, 1, 1))[:N], np.tile(Kss, (rep, 1, 1))[:N], np.tile(gts, (rep, 1, 1))[:N]
+        if sigma > 0 and N > 4096:   # fresh noise for the tiled copies, on the 0.05 px grid of top-20 means
+            rng = np.random.Generator(np.random.PCG64(int(sigma * 10)))
+            c2[4096:] = np.round((c2[4096:] + rng.normal(0, sigma * 0.3, size=c2[4096:].shape)) * 20) / 20
+        c2c, X3c, Ksc = (torch.from_numpy(np.ascontiguousarray(x.astype(np.float32))).cuda() for x in (c2, X3, Ks))
+        res = {}
+        for name, opts, iters in (("mode0_iterative", None, args.steps), ("mode1_hyp512", _lib.BdPnpOpts(1, NH, 2.0, 0, 30), max(1, min(args.steps, 3)))):
+            P, ms = solve(c2c, X3c, Ksc, opts, iters)
+            e = rot_err(P[:, :3, :3], gt[:, :, :3])
+            nh = 1 if opts is None else NH
+            res[name] = {"ms": ms, "queries_per_s": N / ms * 1e3, "hypotheses_per_s": N * nh / ms * 1e3,
+                         "rot_err_deg_median_vs_gt": float(np.median(e)), "rot_err_deg_p95_vs_gt": float(np.percentile(e, 95))}
+            if name == "mode0_iterative":
+                P0 = P
+        if cv2 is not None:
+            nsub = 1000
+            t0 = time.perf_counter()
+            Rs = []
+            for i in range(nsub):
+                ok, rvec, tvec = cv2.solvePnP(X3[i].astype(np.float32), c2[i].astype(np.float32), Ks[i].astype(np.float32), None, flags=cv2.SOLVEPNP_ITERATIVE)
+                Rs.append(cv2.Rodrigues(rvec)[0])
+            dt = time.perf_counter() - t0
+            dd = rot_err(P0[:nsub, :3, :3], np.stack(Rs))
+            res["cv2_solvePnP_iterative_1core"] = {"queries_per_s": nsub / dt, "gpu_mode0_within_1e-3deg_of_cv2": float(np.mean(dd <= 1e-3)),
+                                                   "rot_err_deg_median_vs_gt": float(np.median(rot_err(np.stack(Rs), gt[:nsub, :, :3])))}
+        per_sigma[f"sigma_{sigma:g}px"] = res
+        if sigma == 2.0:
+            headline = res["mode1_hyp512"]
+    clocks = sampler.stop()
+    # ~ fp64 work per hypothesis of mode 1: 6-point DLT (12x12 normal matrix 12*78 FMA, inverse iteration ~2.5 k) + 8-point scoring
+    # (8 x 30) + its share of the LM refit: ~4 kFLOP (fp64).  B200 fp64 (non-tensor) peak ~ 37 TFLOP/s nominal.
+    fp64_flops = headline["hypotheses_per_s"] * 4.0e3
+    print(json.dumps({
+        "metric": "pnp_hypotheses_per_sec", "value": headline["hypotheses_per_s"], "unit": "hypotheses/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": headline["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"PnP isolation (BASELINE configs[4]): {N} queries x {NH} hypotheses, corner noise sigma in {{0,2,5}} px; headline = sigma 2 px, "
+                               "bd_pnp mode 1 (6-point hypotheses scored at 2 px, LM refit on the inliers)", "queries": N, "hypotheses": NH},
+        "roofline": {"bound": "fp64 latency / CUDA cores", "achieved": fp64_flops / 1e12, "peak": 37.0, "unit": "TFLOP/s (fp64, ~4 kFLOP per hypothesis)",
+                     "frac": fp64_flops / 1e12 / 37.0, "traffic": None, "peak_source": "nominal B200 fp64 (no measured fp64 peak on this pool)"},
+        "per_sigma": per_sigma, "cpu_baseline": {"value": per_sigma["sigma_2px"].get("cv2_solvePnP_iterative_1core", {}).get("queries_per_s"),
+                                                 "unit": "queries/s", "cores": 1, "kind": "reference",
+                                                 "sample": "cv2.solvePnP(ITERATIVE) on 1000 of the queries, one host thread (box_utils.py:173-179)"},
+        "e2e": None, "gpu_launches": 0, "clocks": clocks}), flush=True)
     return 0
 
 
@@ -455,6 +786,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="timed loop only (for runs under ncu): no e2e / cpu_baseline legs")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
+                    help="BASELINE.json config: 2 (default; = configs[1], and configs[2] at --gpus 8), 4 (configs[3]: 256 x 16 refs, 336 px), "
+                         "5 (configs[4]: PnP isolation)")
+    ap.add_argument("--micro-batch", type=int, default=32, help="config 4: queries per engine call")
+    ap.add_argument("--pnp-queries", type=int, default=100000, help="config 5: number of queries")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -467,6 +803,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
+        if args.config == 4:
+            return run_config4(args, rank, world, local_rank)
+        if args.config == 5:
+            return run_config5(args, rank, world, local_rank)
         return run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:

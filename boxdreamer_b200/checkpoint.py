@@ -31,15 +31,34 @@ def warp_model(state_dict: dict) -> dict:
     return {(k[len(PREFIX):] if k.startswith(PREFIX) else k): v for k, v in sd.items()}
 
 
-def load_checkpoint(path: str) -> dict:
-    """-> {"decoder.*": fp32 CPU tensors}; keys outside the model (optimizer state, loss buffers, ...) are dropped."""
+def _is_safetensors(path: str) -> bool:
+    """Upstream names its files `.safetensor` (run.py:172-183 downloads `BoxDreamer-vitb.safetensor`, scripts/tools/
+    make_safetensor.py writes `<ckpt>.safetensor`); the library's own suffix is `.safetensors`.  Accept both, and sniff the
+    header (8-byte little-endian length followed by a JSON object) for files with any other name."""
+    if path.endswith((".safetensors", ".safetensor")):
+        return True
+    try:
+        with open(path, "rb") as f:
+            head = f.read(9)
+        n = int.from_bytes(head[:8], "little")
+        return len(head) == 9 and head[8:9] == b"{" and 0 < n < os.path.getsize(path)
+    except OSError:
+        return False
+
+
+def _load_file(path: str) -> dict:
     if not os.path.isfile(path):
         raise FileNotFoundError(path)
-    if path.endswith(".safetensors"):
+    if _is_safetensors(path):
         from safetensors.torch import load_file
-        raw = load_file(path, device="cpu")
-    else:
-        raw = torch.load(path, map_location="cpu", weights_only=False)
+        return load_file(path, device="cpu")
+    # weights_only: tensors and plain containers only -- a checkpoint is untrusted input, never unpickle arbitrary objects
+    return torch.load(path, map_location="cpu", weights_only=True)
+
+
+def load_checkpoint(path: str) -> dict:
+    """-> {"decoder.*": fp32 CPU tensors}; keys outside the model (optimizer state, loss buffers, ...) are dropped."""
+    raw = _load_file(path)
     sd = warp_model(raw)
     return {k: v.detach().to(torch.float32) for k, v in sd.items() if torch.is_tensor(v) and k.startswith("decoder.")}
 
@@ -48,27 +67,44 @@ def load_model(model, path: str | None, dino_path: str | None = None, device=Non
     """Loads decoder (and optionally DINOv2) weights into a boxdreamer_b200.BoxDreamer.  With an initialised process
     group only rank 0 touches the file system; the other ranks pass path=None or simply ignore it."""
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank(group) if world > 1 else 0
+    rank = dist.get_rank(group) if world > 1 else 0       # rank inside `group`; group rank 0 is the loader
     dec_shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     dino_shapes = {k: tuple(v.shape) for k, v in model.rgb_encoder.model.state_dict().items()}
     dec = dino = None
+    error = None
     if rank == 0:
-        dec = load_checkpoint(path)
-        missing = [k for k in dec_shapes if k not in dec]
-        if missing:
-            raise KeyError(f"checkpoint {path} lacks {len(missing)} decoder tensors, e.g. {missing[:3]}")
-        if dino_path is not None:
-            if dino_path.endswith(".safetensors"):
-                from safetensors.torch import load_file
-                dino = load_file(dino_path, device="cpu")
-            else:
-                dino = torch.load(dino_path, map_location="cpu")
+        try:
+            dec = load_checkpoint(path)
+            missing = [k for k in dec_shapes if k not in dec]
+            if missing:
+                raise KeyError(f"checkpoint {path} lacks {len(missing)} decoder tensors, e.g. {missing[:3]}")
+            if dino_path is not None:
+                dino = _load_file(dino_path)
+                missing = [k for k in dino_shapes if k not in dino]
+                if missing:
+                    raise KeyError(f"DINOv2 checkpoint {dino_path} lacks {len(missing)} tensors, e.g. {missing[:3]}")
+        except Exception as exc:   # do not leave the other ranks hanging in the collective: tell them first
+            error = exc
     if world > 1:
-        dec = bdist.broadcast_state(dec, dec_shapes, src=0, device=device, group=group)
-        flag = torch.tensor([1 if (rank == 0 and dino is not None) else 0], device=device)
-        dist.broadcast(flag, src=0, group=group)
-        if int(flag.item()):
-            dino = bdist.broadcast_state(dino, dino_shapes, src=0, device=device, group=group)
+        if device is None:         # NCCL cannot broadcast CPU tensors: default to the model's device
+            backend = dist.get_backend(group)
+            mdev = next(model.parameters()).device
+            device = mdev if (backend == "nccl" and mdev.type == "cuda") else (torch.device("cuda", torch.cuda.current_device())
+                                                                                if backend == "nccl" else None)
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        # status word from the loader: 0 = failed, 1 = decoder only, 2 = decoder + DINOv2
+        flag = torch.tensor([0 if error is not None else (2 if dino is not None else 1)] if rank == 0 else [0], device=device)
+        dist.broadcast(flag, src=src, group=group)
+        status = int(flag.item())
+        if status == 0:
+            if error is not None:
+                raise error
+            raise RuntimeError("load_model: the loading rank failed to read the checkpoint (see its traceback)")
+        dec = bdist.broadcast_state(dec, dec_shapes, src=src, device=device, group=group)
+        if status == 2:
+            dino = bdist.broadcast_state(dino, dino_shapes, src=src, device=device, group=group)
+    elif error is not None:
+        raise error
     model.load_state_dict({k: dec[k] for k in dec_shapes}, strict=True)
     if dino is not None:
         model.rgb_encoder.model.load_state_dict({k: dino[k] for k in dino_shapes}, strict=True)

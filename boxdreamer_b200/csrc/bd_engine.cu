@@ -81,6 +81,15 @@ struct bd_engine {
   long long cat_n[BD_PROF_NCAT] = {0};
 };
 
+// Entry points that take a handle run on the handle's device and restore the caller's current device afterwards.
+struct DevGuard {
+  int prev = -1, want;
+  explicit DevGuard(const bd_engine* e) : want(e ? e->device : -1) {
+    if (want >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != want) cudaSetDevice(want); else prev = -1;
+  }
+  ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 static cudaEvent_t get_event(bd_engine* e) {
   if (!e->ev_pool.empty()) { cudaEvent_t ev = e->ev_pool.back(); e->ev_pool.pop_back(); return ev; }
   cudaEvent_t ev;
@@ -205,6 +214,7 @@ extern "C" int bd_create(bd_handle* out, const bd_config* cfg) {
 
 extern "C" int bd_destroy(bd_handle e) {
   if (!e) return BD_OK;
+  DevGuard dev_guard(e);
   cudaDeviceSynchronize();
   for (void* p : e->allocs) cudaFree(p);
   if (e->host_stream) cudaStreamDestroy(e->host_stream);
@@ -216,6 +226,7 @@ extern "C" int bd_destroy(bd_handle e) {
 
 extern "C" int bd_load_weight(bd_handle e, const char* name, const void* data, const int64_t* shape, int32_t ndim) {
   if (!e || !name || !data || (ndim > 0 && !shape)) return fail(BD_ERR_INVALID, "bd_load_weight: null argument");
+  DevGuard dev_guard(e);
   size_t n = 1;
   std::vector<int64_t> shp;
   for (int i = 0; i < ndim; ++i) { n *= static_cast<size_t>(shape[i]); shp.push_back(shape[i]); }
@@ -257,6 +268,7 @@ static int pack_bf16(bd_engine* e, const std::string& name) {
 
 extern "C" int bd_finalize_weights(bd_handle e) {
   if (!e) return fail(BD_ERR_INVALID, "bd_finalize_weights: null handle");
+  DevGuard dev_guard(e);
   const int64_t d = e->d, pp8 = static_cast<int64_t>(e->patch) * e->patch * 8;
   std::vector<std::string> gemm_w;
   int r;
@@ -363,6 +375,8 @@ static cudaError_t ln_act(bd_engine* e, const float* x, const float* w, const fl
 }
 
 // one pre-LN transformer block on the fp32 residual stream X [L*seq, d]
+// (the LayerNorms stay stand-alone launches: fusing them behind the residual GEMMs was built and measured in round 2 and gains
+// nothing on a power-capped B200, profiles/r02_ln_fusion_measured.txt)
 static int run_block(bd_engine* e, float* X, const std::string& p, int L, int seq, int seq_pad, int heads, int hd, float ln_eps,
                      bool qk_norm, const char* g1, const char* g2, int attn_cat, cudaStream_t s) {
   const int M = L * seq, d = e->d;
@@ -470,12 +484,14 @@ static int decoder_forward_impl(bd_engine* e, const void* bbox_feat, int dtype, 
 
 extern "C" int bd_dino_forward(bd_handle e, const void* images, int32_t dtype, float* feats_out, int32_t L, void* stream) {
   if (!e || !images || !feats_out) return fail(BD_ERR_INVALID, "bd_dino_forward: null argument");
+  DevGuard dev_guard(e);
   return dino_forward_impl(e, images, dtype, feats_out, L, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int bd_decoder_forward(bd_handle e, const void* bbox_feat, int32_t dtype, const float* feats, const int64_t* query_idx,
                                   float* heat_out, float* logits_out, int32_t B, int32_t T, void* stream) {
   if (!e || !bbox_feat || !feats || !query_idx || !heat_out) return fail(BD_ERR_INVALID, "bd_decoder_forward: null argument");
+  DevGuard dev_guard(e);
   return decoder_forward_impl(e, bbox_feat, dtype, feats, false, query_idx, heat_out, logits_out, B, T,
                               reinterpret_cast<cudaStream_t>(stream));
 }
@@ -511,6 +527,7 @@ extern "C" int bd_forward(bd_handle e, const void* images, const void* bbox_feat
                           float* poses_out, const bd_pnp_opts* opts, int32_t B, int32_t T, void* stream) {
   if (!e || !images || !bbox_feat || !query_idx || !bbox3d_q || !K_q || !corners_px || !corners_norm || !poses_out)
     return fail(BD_ERR_INVALID, "bd_forward: null argument");
+  DevGuard dev_guard(e);
   if (B <= 0 || T <= 0 || B > e->Bmax || T > e->Tmax) return fail(BD_ERR_INVALID, "bd_forward: B/T exceed the workspace");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   float* heat = heat_out ? heat_out : e->heat;
@@ -532,6 +549,7 @@ static int forward_host_impl(bd_handle e, const void* images_host, const void* b
   if (!e || !images_host || (!bbox_feat_host && !bbox_px_host) || !query_idx_host || !bbox3d_q_host || !K_q_host || !corners_px_host ||
       !corners_norm_host || !poses_out_host)
     return fail(BD_ERR_INVALID, "bd_forward_host: null argument");
+  DevGuard dev_guard(e);
   if (B <= 0 || T <= 0 || B > e->Bmax || T > e->Tmax) return fail(BD_ERR_INVALID, "bd_forward_host: B/T exceed the workspace");
   const size_t es = in_dtype == BD_BF16 ? 2 : 4;
   const size_t SS = static_cast<size_t>(e->S) * e->S;

@@ -94,7 +94,9 @@ struct PnpOpts {
   uint32_t seed;     // mode 1
   int max_iter;      // LM iterations cap
 };
+// rec (optional, mode 0, n_pts <= 32): packed [B, 28] record {R|t, 8 normalised corners} written by the kernel's epilogue
+// (the payload of the multi-GPU result gather); corners_norm [B, 8, 2] supplies its last 16 floats
 cudaError_t pnp_solve(const float* corners_px, const float* bbox3d, const float* K, float* poses, const PnpOpts& o, int B,
-                      int n_pts, cudaStream_t s);
+                      int n_pts, cudaStream_t s, float* rec = nullptr, const float* corners_norm = nullptr);
 
 }  // namespace bd

@@ -599,6 +599,318 @@ __global__ void __launch_bounds__(64) pnp_iterative_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
+// PnP, reference-parity mode, one WARP per query (n_pts <= 32: the timed path, 8 box corners).  Same algorithm as
+// pnp_dlt_init + pnp_lm above -- DLT normal matrix, smallest eigenvector by Rayleigh-shifted inverse iteration on a Cholesky
+// factor, Newton polar, Levenberg-Marquardt to convergence, all fp64 -- but cooperative: the 12x12 work is spread over 12
+// lanes (column-parallel Cholesky, column-oriented substitutions, matrix and factor in shared memory), every lane owns one
+// point in the LM loop (its Jacobian rows and residual), the 27 sums of the normal equations are formed in point order through
+// shared memory, and the 6x6 solve / rotation update run redundantly in registers so that every decision is warp-uniform.
+// The thread-per-query kernel kept its 12x12 arrays in local memory and ran 64 queries on one SM (1.2 ms per batch of 64 at
+// BASELINE config 2); this one spreads the batch over B/4 CTAs and takes tens of microseconds.
+static constexpr int PW_WARPS = 4;
+static constexpr int PW_MAXPTS = 32;
+struct PnpW {
+  double X[PW_MAXPTS][3], uv[PW_MAXPTS][2];
+  double A[144], L[144];
+  double x[12];
+  double red[27][PW_MAXPTS];
+  double tot[28];
+};
+
+__device__ __forceinline__ double w_sum(double v) {   // all-lane sum (butterfly)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// L L^T = A - mu*I, column by column: lane i computes entry (i, j); returns a warp-uniform flag
+__device__ bool w_chol12(PnpW& w, double mu, int lane) {
+  for (int j = 0; j < 12; ++j) {
+    double v = 0.0;
+    if (lane >= j && lane < 12) {
+      v = w.A[j * 12 + lane] - (lane == j ? mu : 0.0);
+      for (int k = 0; k < j; ++k) v -= w.L[lane * 12 + k] * w.L[j * 12 + k];
+    }
+    const double d = __shfl_sync(0xffffffffu, v, j);
+    if (!(d > 1e-300)) return false;
+    const double sd = sqrt(d);
+    if (lane == j) w.L[j * 13] = sd;
+    else if (lane > j && lane < 12) w.L[lane * 12 + j] = v / sd;
+    __syncwarp();
+  }
+  return true;
+}
+
+// x <- normalised (L L^T)^-1 x with the sign kept; lane i < 12 holds component i.  Returns a warp-uniform flag.
+__device__ bool w_chol12_step(PnpW& w, int lane) {
+  const double xi = lane < 12 ? w.x[lane] : 0.0;
+  double v = xi, yi = 0.0;
+  for (int k = 0; k < 12; ++k) {          // forward substitution, column oriented
+    double yk = 0.0;
+    if (lane == k) { yk = v / w.L[k * 13]; yi = yk; }
+    yk = __shfl_sync(0xffffffffu, yk, k);
+    if (lane > k && lane < 12) v -= w.L[lane * 12 + k] * yk;
+  }
+  v = yi;
+  double zi = 0.0;
+  for (int k = 11; k >= 0; --k) {         // backward substitution with L^T
+    double zk = 0.0;
+    if (lane == k) { zk = v / w.L[k * 13]; zi = zk; }
+    zk = __shfl_sync(0xffffffffu, zk, k);
+    if (lane < k) v -= w.L[k * 12 + lane] * zk;
+  }
+  const double n = sqrt(w_sum(lane < 12 ? zi * zi : 0.0));
+  const double dot = w_sum(lane < 12 ? xi * zi : 0.0);
+  if (!(n > 0.0) || !isfinite(n)) return false;
+  const double sc = (dot < 0.0 ? -1.0 : 1.0) / n;
+  __syncwarp();
+  if (lane < 12) w.x[lane] = zi * sc;
+  __syncwarp();
+  return true;
+}
+
+__device__ bool w_smallest_eigvec(PnpW& w, int lane) {
+  double tr = 0.0;
+  for (int i = 0; i < 12; ++i) tr += w.A[i * 13];
+  if (!(tr > 0.0)) return false;
+  if (!w_chol12(w, -1e-10 * tr, lane)) return false;
+  {
+    double n0 = 0.0;
+    for (int i = 0; i < 12; ++i) n0 += 1.0 / ((1.0 + i) * (1.0 + i));
+    if (lane < 12) w.x[lane] = (1.0 / (1.0 + lane)) / sqrt(n0);
+    __syncwarp();
+  }
+  for (int it = 0; it < 3; ++it)
+    if (!w_chol12_step(w, lane)) return false;
+  double mu_prev = -1e-10 * tr;
+  for (int it = 0; it < 40; ++it) {
+    double yv = 0.0, xi = 0.0;
+    if (lane < 12) {
+      for (int k = 0; k < 12; ++k) yv += w.A[lane * 12 + k] * w.x[k];
+      xi = w.x[lane];
+    }
+    const double rho = w_sum(yv * xi);
+    const double dr = yv - rho * xi;
+    const double r = sqrt(w_sum(lane < 12 ? dr * dr : 0.0));
+    if (r <= 1e-15 * tr) return true;
+    double mu = rho - 1.5 * r;
+    bool ok = w_chol12(w, mu, lane);
+    if (!ok) {
+      mu = 0.5 * (mu + mu_prev);
+      ok = w_chol12(w, mu, lane);
+      if (!ok) { mu = mu_prev; ok = w_chol12(w, mu, lane); }
+      if (!ok) return false;
+    }
+    mu_prev = mu < mu_prev ? mu_prev : mu;
+    if (!w_chol12_step(w, lane)) return false;
+    const double dx = lane < 12 ? w.x[lane] - xi : 0.0;
+    if (w_sum(dx * dx) < 1e-28) return true;
+  }
+  return false;
+}
+
+// element j of the two DLT rows of point i (normalised image coordinates xn, yn)
+__device__ __forceinline__ void w_dlt_rows(const PnpW& w, int i, int j, double xn, double yn, double& r1, double& r2) {
+  const int c = j & 3, blk = j >> 2;
+  const double h = c < 3 ? w.X[i][c] : 1.0;
+  r1 = blk == 0 ? h : (blk == 2 ? -xn * h : 0.0);
+  r2 = blk == 1 ? h : (blk == 2 ? -yn * h : 0.0);
+}
+
+// pixel residual / camera-frame point / squared error of this lane's point
+__device__ __forceinline__ double w_point_eval(const PnpW& w, int i, const double (&R)[3][3], const double (&t)[3], double fx, double fy,
+                                               double cx, double cy, double (&res)[2], double (&Xc)[3]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) Xc[a] = R[a][0] * w.X[i][0] + R[a][1] * w.X[i][1] + R[a][2] * w.X[i][2] + t[a];
+  res[0] = fx * Xc[0] / Xc[2] + cx - w.uv[i][0];
+  res[1] = fy * Xc[1] / Xc[2] + cy - w.uv[i][1];
+  return res[0] * res[0] + res[1] * res[1];
+}
+// sum over the points in point order (every lane returns the same value)
+__device__ __forceinline__ double w_ordered_sum(PnpW& w, int n, int lane, double mine) {
+  __syncwarp();
+  if (lane < n) w.red[0][lane] = mine;
+  __syncwarp();
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += w.red[0][i];
+  return s;
+}
+
+__global__ void __launch_bounds__(PW_WARPS * 32) pnp_iterative_warp_kernel(const float* __restrict__ corners, const float* __restrict__ bbox3d,
+                                                                         const float* __restrict__ Kmat, float* __restrict__ poses,
+                                                                         float* __restrict__ rec, const float* __restrict__ corners_norm,
+                                                                         int B, int n, int max_iter) {
+  __shared__ PnpW sw[PW_WARPS];
+  const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * PW_WARPS + wq;
+  if (q >= B) return;
+  PnpW& w = sw[wq];
+  if (lane < n) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) w.X[lane][a] = static_cast<double>(bbox3d[(static_cast<long long>(q) * n + lane) * 3 + a]);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) w.uv[lane][a] = static_cast<double>(corners[(static_cast<long long>(q) * n + lane) * 2 + a]);
+  }
+  const float* Kq = Kmat + static_cast<long long>(q) * 9;
+  const double fx = Kq[0], fy = Kq[4], cx = Kq[2], cy = Kq[5];
+  __syncwarp();
+  // ---- DLT normal matrix: entry e = (a, b), summed over the points in order
+  for (int e = lane; e < 144; e += 32) {
+    const int a = e / 12, b = e % 12;
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double xn = (w.uv[i][0] - cx) / fx, yn = (w.uv[i][1] - cy) / fy;
+      double a1, a2, b1, b2;
+      w_dlt_rows(w, i, a, xn, yn, a1, a2);
+      w_dlt_rows(w, i, b, xn, yn, b1, b2);
+      acc += a1 * b1 + a2 * b2;
+    }
+    w.A[e] = acc;
+  }
+  __syncwarp();
+  double R[3][3], t[3];
+  {
+    double Rd[3][3], td[3];
+    const bool have = w_smallest_eigvec(w, lane);
+    if (!have) {   // rare: cyclic Jacobi by one lane on local copies (same fallback as the thread-per-query kernel)
+      __syncwarp();
+      if (lane == 0) {
+        double Aj[144], Vj[144];
+        for (int i = 0; i < 144; ++i) Aj[i] = w.A[i];
+        jacobi_eig_sym12(Aj, Vj);
+        int kmin = 0;
+        for (int k = 1; k < 12; ++k)
+          if (Aj[k * 13] < Aj[kmin * 13]) kmin = k;
+        for (int i = 0; i < 12; ++i) w.x[i] = Vj[i * 12 + kmin];
+      }
+      __syncwarp();
+    }
+    for (int a = 0; a < 3; ++a) {
+      for (int b = 0; b < 3; ++b) Rd[a][b] = w.x[a * 4 + b];
+      td[a] = w.x[a * 4 + 3];
+    }
+    if (det3(Rd) < 0.0) {
+      for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) Rd[a][b] = -Rd[a][b];
+        td[a] = -td[a];
+      }
+    }
+    double nrm = 0.0;
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) nrm += Rd[a][b] * Rd[a][b];
+    nrm = sqrt(nrm);
+    const double sc = sqrt(3.0) / fmax(nrm, 1e-300);
+    for (int a = 0; a < 3; ++a) {
+      for (int b = 0; b < 3; ++b) R[a][b] = Rd[a][b] * sc;
+      t[a] = td[a] * sc;
+    }
+    nearest_rotation(R, 60);
+  }
+  // ---- Levenberg-Marquardt (pnp_lm): lane i owns point i
+  const int pi = lane < n ? lane : 0;
+  double res[2], Xc[3];
+  double lam = 1e-3;
+  double cost = w_ordered_sum(w, n, lane, w_point_eval(w, pi, R, t, fx, fy, cx, cy, res, Xc));
+  for (int it = 0; it < max_iter; ++it) {
+    {
+      const double x = Xc[0], y = Xc[1], z = Xc[2];
+      const double du[3] = {fx / z, 0.0, -fx * x / (z * z)};
+      const double dv[3] = {0.0, fy / z, -fy * y / (z * z)};
+      const double Y[3] = {x - t[0], y - t[1], z - t[2]};
+      const double W[3][3] = {{0, Y[2], -Y[1]}, {-Y[2], 0, Y[0]}, {Y[1], -Y[0], 0}};
+      double ju[6], jv[6];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        ju[a] = du[0] * W[0][a] + du[1] * W[1][a] + du[2] * W[2][a];
+        jv[a] = dv[0] * W[0][a] + dv[1] * W[1][a] + dv[2] * W[2][a];
+        ju[3 + a] = du[a];
+        jv[3 + a] = dv[a];
+      }
+      __syncwarp();
+      if (lane < n) {
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) w.red[e++][lane] = ju[a] * res[0] + jv[a] * res[1];
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int b = a; b < 6; ++b) w.red[e++][lane] = ju[a] * ju[b] + jv[a] * jv[b];
+      }
+      __syncwarp();
+      if (lane < 27) {
+        double sacc = 0.0;
+        for (int i = 0; i < n; ++i) sacc += w.red[lane][i];
+        w.tot[lane] = sacc;
+      }
+      __syncwarp();
+    }
+    double H[6][6], g[6];
+    {
+      int e = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) g[a] = w.tot[e++];
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) { H[a][b] = w.tot[e++]; H[b][a] = H[a][b]; }
+    }
+    bool improved = false;
+    double step = 0.0, dc = 0.0;
+    for (int tr = 0; tr < 12; ++tr) {
+      double delta[6];
+      if (!solve6(H, g, lam, delta)) { lam *= 10.0; continue; }
+      const double wv[3] = {delta[0], delta[1], delta[2]};
+      double E[3][3], Rn[3][3], tn[3];
+      rodrigues_exp(wv, E);
+      for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) Rn[a][b] = E[a][0] * R[0][b] + E[a][1] * R[1][b] + E[a][2] * R[2][b];
+        tn[a] = t[a] + delta[3 + a];
+      }
+      double resn[2], Xcn[3];
+      const double cn = w_ordered_sum(w, n, lane, w_point_eval(w, pi, Rn, tn, fx, fy, cx, cy, resn, Xcn));
+      if (isfinite(cn) && cn <= cost) {
+        improved = true;
+        for (int a = 0; a < 6; ++a) step += delta[a] * delta[a];
+        step = sqrt(step);
+        dc = cost - cn;
+        cost = cn;
+        for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) R[a][b] = Rn[a][b]; t[a] = tn[a]; }
+        res[0] = resn[0]; res[1] = resn[1];
+        Xc[0] = Xcn[0]; Xc[1] = Xcn[1]; Xc[2] = Xcn[2];
+        lam = fmax(lam * 0.1, 1e-12);
+        break;
+      }
+      lam *= 10.0;
+    }
+    if (!improved || step < 1e-13 || dc <= 1e-15 * cost + 1e-300) break;
+  }
+  nearest_rotation(R, 4);
+  if (lane == 0) {
+    bool ok = true;
+    for (int a = 0; a < 3; ++a) {
+      ok = ok && isfinite(t[a]);
+      for (int b = 0; b < 3; ++b) ok = ok && isfinite(R[a][b]);
+    }
+    float* P = poses + static_cast<long long>(q) * 16;
+    for (int i = 0; i < 16; ++i) P[i] = 0.f;  // failure => zero pose (box_utils.py:136,194-197)
+    if (ok) {
+      for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) P[a * 4 + b] = static_cast<float>(R[a][b]);
+        P[a * 4 + 3] = static_cast<float>(t[a]);
+      }
+      P[15] = 1.0f;
+    }
+  }
+  // packed result record of the multi-GPU gather: [R|t (12, row-major 3x4), 8 normalised corners (16)] (dist.py RECORD)
+  if (rec != nullptr) {
+    __syncwarp();
+    float* rq = rec + static_cast<long long>(q) * 28;
+    if (lane < 12) rq[lane] = poses[static_cast<long long>(q) * 16 + lane];
+    else if (lane < 28 && corners_norm != nullptr) rq[lane] = corners_norm[static_cast<long long>(q) * 16 + (lane - 12)];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // PnP, hypothesis mode (the robust counterpart of cv2.solvePnPRansac, box_utils.py:158-166 / 266-275): one warp per
 // query, one lane per hypothesis.  Hypotheses: every 6-point subset solved from scratch (DLT -> LM), then every 5- and
 // 4-point subset (and, beyond those, seeded random 5-subsets) refitted from the all-point solution with a few LM steps; each is scored on ALL points (inlier count at thr_px, then truncated squared error), the warp arg-max wins and
@@ -861,7 +1173,7 @@ cudaError_t pose_metrics(const float* pose_pred, const float* pose_gt, const flo
 }
 
 cudaError_t pnp_solve(const float* corners_px, const float* bbox3d, const float* K, float* poses, const PnpOpts& o, int B,
-                      int n_pts, cudaStream_t s) {
+                      int n_pts, cudaStream_t s, float* rec, const float* corners_norm) {
   if (B <= 0) return cudaSuccess;
   if (n_pts < 6 || n_pts > PNP_MAXPTS) return cudaErrorInvalidValue;
   if (o.mode != 0 && o.mode != 1) return cudaErrorNotSupported;
@@ -869,9 +1181,17 @@ cudaError_t pnp_solve(const float* corners_px, const float* bbox3d, const float*
   if (o.mode == 1) {
     const int n_hyp = o.n_hyp > 0 ? o.n_hyp : 154;
     const float thr = o.thr_px > 0.f ? o.thr_px : 2.0f;
+    if (rec != nullptr) return cudaErrorNotSupported;
     pnp_hypothesis_kernel<<<(B + 3) / 4, 128, 0, s>>>(corners_px, bbox3d, K, poses, B, n_pts, n_hyp, thr, o.seed, max_iter);
     return cudaGetLastError();
   }
+  static const bool thread_kernel = getenv("BD_PNP_THREAD") != nullptr;   // debug switch: the thread-per-query kernel
+  if (n_pts <= PW_MAXPTS && !thread_kernel) {
+    pnp_iterative_warp_kernel<<<(B + PW_WARPS - 1) / PW_WARPS, PW_WARPS * 32, 0, s>>>(corners_px, bbox3d, K, poses, rec, corners_norm, B, n_pts,
+                                                                                    max_iter);
+    return cudaGetLastError();
+  }
+  if (rec != nullptr) return cudaErrorNotSupported;
   pnp_iterative_kernel<<<(B + 63) / 64, 64, 0, s>>>(corners_px, bbox3d, K, poses, B, n_pts, max_iter);
   return cudaGetLastError();
 }

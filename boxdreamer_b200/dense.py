@@ -175,6 +175,9 @@ def process_dense_input(data, pose_feat, frames, camera_mask, rgb_feature, image
     return data, pose_feat, frames, camera_mask, rgb_feature, image_masks
 
 
+MAX_POOLED_POINTS = 64   # PNP_MAXPTS of csrc/post.cu (pooled robust PnP: n_sub sub-batches x 8 corners)
+
+
 def process_multi_round(data, pose_feat, frames, camera_mask, rgb_feature, image_masks, decoder, dense_cfg, bbox_representation,
                         pooled_pose_fn):
     """Coarse round over sub-batches of the references -> pooled robust PnP -> fine round on the `fine_topk` references
@@ -192,6 +195,12 @@ def process_multi_round(data, pose_feat, frames, camera_mask, rgb_feature, image
     K_q = data["non_ndc_intrinsics"][camera_mask]
     bbox3d_q = data["bbox_3d"][camera_mask]
     sub = _cfg(dense_cfg, "sub_batch_size")
+    n_ref = frames.shape[1] - 1
+    n_sub_planned = (n_ref + sub - 1) // sub
+    if n_sub_planned * 8 > MAX_POOLED_POINTS:   # checked before any GPU work: the coarse decoder round is the expensive part
+        raise ValueError(
+            f"dense multi-round: {n_ref} references in sub-batches of {sub} pool {n_sub_planned * 8} 2D-3D pairs, but bd_pnp takes at most "
+            f"{MAX_POOLED_POINTS}; enable dense_cfg.filter_enable (filter_topk <= {MAX_POOLED_POINTS // 8 * sub}) or raise sub_batch_size")
     g_pose, g_frames, g_mask, g_rgb, g_img_masks = sub_batchify(pose_feat, frames, camera_mask, rgb_feature, image_masks, sub)
     n_sub = g_pose.shape[1]
     if _cfg(dense_cfg, "dense_mem_friendly"):

@@ -49,14 +49,15 @@ def unflatten_state(flat: torch.Tensor, shapes: dict) -> dict:
 
 
 def broadcast_state(sd: dict | None, shapes: dict, src: int = 0, device=None, group=None) -> dict:
-    """Rank `src` passes its state dict; every rank returns an identical one (a single collective)."""
+    """Rank `src` (a GLOBAL rank, as torch.distributed.broadcast takes it) passes its state dict; every rank of `group`
+    returns an identical one (a single collective)."""
     total = 0
     for shp in shapes.values():
         n = 1
         for s in shp:
             n *= int(s)
         total += n
-    rank = dist.get_rank(group)
+    rank = dist.get_rank()   # global rank: `src` is global too (a group rank would be wrong for non-default groups)
     if rank == src:
         flat, _ = flatten_state(sd, list(shapes.keys()))
         flat = flat.to(device) if device is not None else flat

@@ -66,6 +66,20 @@ def setup_camera_params(config):
 # engine wrapper
 
 
+def _on_device(fn):
+    """Runs an Engine method with the engine's device current (kernels, `current_stream()` and allocations then all refer to
+    the device the workspace lives on, whatever device the caller had selected)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        if torch.cuda.current_device() == self.device:
+            return fn(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapper
+
+
 class Engine:
     """One bd_handle: workspace for (max_batch, max_views) at one precision on the current device."""
 
@@ -79,6 +93,7 @@ class Engine:
         self.cfg = _lib.BdConfig(img_size, patch, d_model, dec_layers, dec_heads, dino_layers, dino_heads,
                                  dino_registers, 37, precision, attn_variant, max_batch, max_views)
         self.handle = C.c_void_p()
+        self.device = torch.cuda.current_device()
         _lib.check(self.lib.bd_create(C.byref(self.handle), C.byref(self.cfg)), "bd_create")
         self.precision = precision
         self.max_batch, self.max_views = max_batch, max_views
@@ -97,6 +112,7 @@ class Engine:
         except Exception:
             pass
 
+    @_on_device
     def load_weights(self, named_tensors: dict):
         for name, t in named_tensors.items():
             t = t.detach().to(torch.float32).contiguous()
@@ -116,6 +132,7 @@ class Engine:
             return _lib.BD_BF16
         raise TypeError(f"unsupported dtype {t.dtype}")
 
+    @_on_device
     def dino_forward(self, images):
         L = images.shape[0]
         feats = torch.empty(L, self.P, self.d, device=images.device, dtype=torch.float32)
@@ -123,6 +140,7 @@ class Engine:
                                             _lib.stream_ptr()), "bd_dino_forward")
         return feats
 
+    @_on_device
     def decoder_forward(self, bbox_feat, feats, query_idx, want_logits=False):
         B, T = bbox_feat.shape[:2]
         heat = torch.empty(B, 8, self.S, self.S, device=bbox_feat.device, dtype=torch.float32)
@@ -133,6 +151,7 @@ class Engine:
                                                _lib.stream_ptr()), "bd_decoder_forward")
         return (heat, logits) if want_logits else heat
 
+    @_on_device
     def corners_topk(self, heat, want_idx=False):
         B, _, S, _ = heat.shape
         px = torch.empty(B, 8, 2, device=heat.device, dtype=torch.float32)
@@ -142,6 +161,7 @@ class Engine:
                                             _lib.stream_ptr()), "bd_corners_topk")
         return (px, nm, idx) if want_idx else (px, nm)
 
+    @_on_device
     def pnp(self, corners_px, bbox3d, K, opts=None):
         B, n = corners_px.shape[:2]
         poses = torch.empty(B, 4, 4, device=corners_px.device, dtype=torch.float32)
@@ -150,6 +170,7 @@ class Engine:
                                    _lib.stream_ptr()), "bd_pnp")
         return poses
 
+    @_on_device
     def forward(self, images, bbox_feat, query_idx, bbox3d_q, K_q, want_heat=True, opts=None):
         B, T = images.shape[:2]
         dev = images.device
@@ -163,6 +184,7 @@ class Engine:
                                        _lib.ptr(nm), _lib.ptr(poses), o, B, T, _lib.stream_ptr()), "bd_forward")
         return heat, px, nm, poses
 
+    @_on_device
     def forward_host(self, images, bbox_feat, query_idx, bbox3d_q, K_q, want_heat=False, opts=None):
         """Host tensors in, host tensors out (H2D/D2H inside the call)."""
         B, T = images.shape[:2]
@@ -177,6 +199,7 @@ class Engine:
         return heat, px, nm, poses
 
 
+    @_on_device
     def forward_host_px(self, images, bbox_px, query_idx, bbox3d_q, K_q, want_heat=False, opts=None):
         """forward_host with the reference heat maps rasterised on the device from bbox_px [B,T,8,2] (host, fp32)."""
         B, T = images.shape[:2]
@@ -332,7 +355,7 @@ class DinoV2Wrapper:
         for p in self.model.parameters():
             p.requires_grad = False
         if ckpt_path is not None and os.path.isfile(str(ckpt_path)):
-            self.model.load_state_dict(torch.load(ckpt_path, map_location="cpu"))
+            self.model.load_state_dict(torch.load(ckpt_path, map_location="cpu", weights_only=True))
         self._owner = None
 
     def get_device(self):
@@ -407,7 +430,7 @@ class BoxDreamer(nn.Module):
         self._bump()
 
     def _pick_precision(self, t: torch.Tensor) -> int:
-        p = self.precision
+        p = self.precision or getattr(self, "_forward_precision", None)   # fixed once per forward (see forward())
         if p is None:
             low = t.dtype in (torch.bfloat16, torch.float16) or torch.is_autocast_enabled()
             p = "bf16" if low else "exact"
@@ -480,6 +503,17 @@ class BoxDreamer(nn.Module):
         if tuple(images.shape[-2:]) != (self.image_size, self.image_size):
             raise AssertionError(f"H and W should be equal to img_size {self.image_size}, got {tuple(images.shape[-2:])}")
         query_idx = query_idx.to(device=dev, dtype=torch.int64).contiguous()
+        # the precision is decided once, from the images (or self.precision): later engine look-ups keyed by fp32 intermediates
+        # (heat maps, pooled proposals of the dense path) must not build a second engine at another precision
+        if self.precision is None:
+            low = images.dtype in (torch.bfloat16, torch.float16) or torch.is_autocast_enabled()
+            self._forward_precision = "bf16" if low else "exact"
+        try:
+            return self._forward_impl(data, poses, images, B, T, query_idx, dev)
+        finally:
+            self._forward_precision = None
+
+    def _forward_impl(self, data, poses, images, B, T, query_idx, dev):
         camera_mask = torch.zeros(poses.shape[:2], dtype=torch.bool, device=dev)
         camera_mask[torch.arange(B, device=dev), query_idx] = True
         data["camera_mask"] = camera_mask.clone()

@@ -21,12 +21,51 @@ def test_load_checkpoint_formats(tmp_path):
     torch.save({"state_dict": {**{"BoxDreamer." + k: v for k, v in sd.items()}, "loss.weight": torch.ones(1)}, "epoch": 3}, p2)
     p3 = str(tmp_path / "plain.pth")
     torch.save(sd, p3)
-    for p in (p1, p2, p3):
+    p4 = str(tmp_path / "BoxDreamer-vitb.safetensor")      # the upstream file name (run.py:172-183: singular suffix)
+    save_file({k: v.contiguous() for k, v in sd.items()}, p4)
+    p5 = str(tmp_path / "weights.bin")                    # safetensors content under a foreign name: sniffed from the header
+    save_file({k: v.contiguous() for k, v in sd.items()}, p5)
+    for p in (p1, p2, p3, p4, p5):
         got = ck.load_checkpoint(p)
         assert set(got.keys()) == set(sd.keys())          # safetensors returns its keys sorted; load_model orders by the model
         assert all(torch.equal(got[k], sd[k]) for k in sd)
     with pytest.raises(FileNotFoundError):
         ck.load_checkpoint(str(tmp_path / "missing.ckpt"))
+
+
+def test_untrusted_pickle_is_refused(tmp_path):
+    """torch checkpoints are read with weights_only=True: a pickle that needs arbitrary code is rejected, not executed."""
+    class Boom:
+        def __reduce__(self):
+            return (os.system, ("true",))
+    p = str(tmp_path / "evil.ckpt")
+    torch.save({"state_dict": {"decoder.x": torch.ones(1)}, "hook": Boom()}, p)
+    with pytest.raises(Exception):
+        ck.load_checkpoint(p)
+
+
+def _worker_bad(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = BoxDreamer(make_config(224, num_layers=1))
+        try:
+            ck.load_model(model, "/nonexistent/ckpt.safetensor" if rank == 0 else None)
+            ret[rank] = "no error"
+        except FileNotFoundError:
+            ret[rank] = "FileNotFoundError"
+        except RuntimeError:
+            ret[rank] = "RuntimeError"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bad_path_fails_on_every_rank_instead_of_hanging():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_bad, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert dict(ret) == {0: "FileNotFoundError", 1: "RuntimeError"}
 
 
 def _free_port():

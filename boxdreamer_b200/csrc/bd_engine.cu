@@ -71,6 +71,12 @@ struct bd_engine {
   cudaStream_t host_stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[8] = {nullptr};
+  // CUDA graphs of the launch chain (graph_run): one executable per (stage, shape, options), captured on `cap_stream`
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int calls = 0; bool unusable = false; long long launches = 0; };
+  std::map<std::vector<long long>, GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;
+  int graph_max_views = 24;   // bd_forward (device pointers): largest B*T that is staged and replayed; BOXDREAMER_B200_GRAPH_MAX_VIEWS
+  bool graphs_on = true;      // BOXDREAMER_B200_GRAPHS=0 switches every replay off
   // instrumentation: kernel launch counter and optional per-category CUDA-event timing
   long long launches = 0;
   bool profile = false;
@@ -95,6 +101,11 @@ static cudaEvent_t get_event(bd_engine* e) {
   cudaEvent_t ev;
   cudaEventCreate(&ev);
   return ev;
+}
+
+static void drop_graphs(bd_engine* e) {
+  for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  e->graphs.clear();
 }
 
 // launches `expr` (a cudaError_t launcher that enqueues `nk` kernels) under category `cat`
@@ -161,6 +172,8 @@ extern "C" int bd_create(bd_handle* out, const bd_config* cfg) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, e->device));
   e->tc = cfg->precision == BD_PRECISION_BF16;
+  if (const char* ev = getenv("BOXDREAMER_B200_GRAPHS")) e->graphs_on = atoi(ev) != 0;
+  if (const char* ev = getenv("BOXDREAMER_B200_GRAPH_MAX_VIEWS")) e->graph_max_views = atoi(ev);
   if (e->tc && prop.major != 10) {
     delete e;
     return fail(BD_ERR_UNSUPPORTED, "bd_create: the bf16 tensor path needs an sm_100 (Blackwell) device");
@@ -220,6 +233,8 @@ extern "C" int bd_destroy(bd_handle e) {
   if (e->host_stream) cudaStreamDestroy(e->host_stream);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   for (int i = 0; i < 8; ++i) if (e->copy_ev[i]) cudaEventDestroy(e->copy_ev[i]);
+  drop_graphs(e);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   delete e;
   return BD_OK;
 }
@@ -269,6 +284,7 @@ static int pack_bf16(bd_engine* e, const std::string& name) {
 extern "C" int bd_finalize_weights(bd_handle e) {
   if (!e) return fail(BD_ERR_INVALID, "bd_finalize_weights: null handle");
   DevGuard dev_guard(e);
+  drop_graphs(e);   // captured launch chains hold the addresses of the packed weights
   const int64_t d = e->d, pp8 = static_cast<int64_t>(e->patch) * e->patch * 8;
   std::vector<std::string> gemm_w;
   int r;
@@ -482,6 +498,78 @@ static int decoder_forward_impl(bd_engine* e, const void* bbox_feat, int dtype, 
   return BD_OK;
 }
 
+// ---- CUDA graphs of the launch chain --------------------------------------------------------------------------------------
+// A forward is ~220 launches, each with host-side work (tensor-map encoding, weight look-ups): at batch 1 the host, not the GPU,
+// sets the latency.  `body(stream)` enqueues a stage that reads and writes engine-owned buffers only, so its launches can be
+// captured once per key (stage, shape, options) and replayed with one cudaGraphLaunch.  The first call of a key runs eagerly
+// (one-time kernel attributes, lazy allocations); the second is captured on `cap_stream` -- the caller's stream may be the
+// legacy default stream, which cannot be captured -- and the executable graph is launched into the caller's stream.  Profiling
+// (per-launch events) and BOXDREAMER_B200_GRAPHS=0 take the eager path.
+template <typename F>
+static int graph_run(bd_engine* e, const std::vector<long long>& key, cudaStream_t s, F&& body) {
+  if (!e->graphs_on || e->profile) return body(s);
+  bd_engine::GraphEntry& g = e->graphs[key];
+  if (g.exec) {
+    CK(cudaGraphLaunch(g.exec, s));
+    e->launches += g.launches;
+    return BD_OK;
+  }
+  if (g.unusable || g.calls++ == 0) return body(s);
+  if (!e->cap_stream) CK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+  const long long l0 = e->launches;
+  CK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+  const int r = body(e->cap_stream);
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+  const long long n = e->launches - l0;
+  e->launches = l0;   // nothing has run yet
+  if (r == BD_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&g.exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  if (r != BD_OK || ce != cudaSuccess || !g.exec) {   // not capturable on this driver / with these options: stay eager for this key
+    cudaGetLastError();
+    g.exec = nullptr;
+    g.unusable = true;
+    return r != BD_OK ? r : body(s);
+  }
+  g.launches = n;
+  CK(cudaGraphLaunch(g.exec, s));
+  e->launches += n;
+  return BD_OK;
+}
+
+static PnpOpts to_opts(const bd_pnp_opts* o) {
+  PnpOpts p{0, 0, 1.0f, 0u, 30};
+  if (o) { p.mode = o->mode; p.n_hyp = o->n_hyp; p.thr_px = o->thr_px; p.seed = o->seed; p.max_iter = o->max_iter; }
+  return p;
+}
+
+static int ensure_staging(bd_engine* e) {
+  if (e->in_images) return BD_OK;
+  const size_t SS = static_cast<size_t>(e->S) * e->S, Lm = e->Lmax;
+  DALLOC(e->in_images, Lm * 3 * SS * 4);
+  DALLOC(e->in_bbox, Lm * 8 * SS * 4);
+  return BD_OK;
+}
+
+// The two stages of a forward on the engine-owned staging buffers (in_images / in_bbox / qidx / bbox3d_q / K_q -> heat,
+// corners_px, corners_norm, poses): the encoder over images [img0, img0 + L), and decoder + corner extraction + PnP.
+static int encoder_body(bd_engine* e, int dtype, int img0, int L, cudaStream_t s) {
+  const size_t img_b = static_cast<size_t>(3) * e->S * e->S * (dtype == BD_BF16 ? 2 : 4);
+  return dino_forward_impl(e, static_cast<char*>(e->in_images) + img0 * img_b, dtype, e->tc ? nullptr : e->feats, L, s, img0);
+}
+static int decoder_post_body(bd_engine* e, int dtype, int B, int T, const PnpOpts& po, cudaStream_t s) {
+  int r = decoder_forward_impl(e, e->in_bbox, dtype, e->feats, e->tc, e->qidx, e->heat, nullptr, B, T, s);
+  if (r != BD_OK) return r;
+  LAUNCH(BD_PROF_TOPK, 1, corners_topk(e->heat, e->corners_px, e->corners_norm, nullptr, B, 8, e->S, s));
+  LAUNCH(BD_PROF_PNP, 1, pnp_solve(e->corners_px, e->bbox3d_q, e->K_q, e->poses, po, B, 8, s));
+  return BD_OK;
+}
+static std::vector<long long> graph_key(int stage, int dtype, int a, int b, const PnpOpts& po) {
+  long long thr_bits = 0;
+  memcpy(&thr_bits, &po.thr_px, sizeof(float));
+  return {stage, dtype, a, b, po.mode, po.n_hyp, thr_bits, po.seed, po.max_iter};
+}
+
 extern "C" int bd_dino_forward(bd_handle e, const void* images, int32_t dtype, float* feats_out, int32_t L, void* stream) {
   if (!e || !images || !feats_out) return fail(BD_ERR_INVALID, "bd_dino_forward: null argument");
   DevGuard dev_guard(e);
@@ -505,12 +593,6 @@ extern "C" int bd_corners_topk(bd_handle e, const float* heat, float* corners_px
   return BD_OK;
 }
 
-static PnpOpts to_opts(const bd_pnp_opts* o) {
-  PnpOpts p{0, 0, 1.0f, 0u, 30};
-  if (o) { p.mode = o->mode; p.n_hyp = o->n_hyp; p.thr_px = o->thr_px; p.seed = o->seed; p.max_iter = o->max_iter; }
-  return p;
-}
-
 extern "C" int bd_pnp(bd_handle e, const float* corners_px, const float* bbox3d, const float* K, float* poses_out,
                       const bd_pnp_opts* opts, int32_t B, int32_t n_pts, void* stream) {
   (void)e;
@@ -530,14 +612,36 @@ extern "C" int bd_forward(bd_handle e, const void* images, const void* bbox_feat
   DevGuard dev_guard(e);
   if (B <= 0 || T <= 0 || B > e->Bmax || T > e->Tmax) return fail(BD_ERR_INVALID, "bd_forward: B/T exceed the workspace");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const PnpOpts po = to_opts(opts);
+  if (po.mode != 0 && po.mode != 1) return fail(BD_ERR_UNSUPPORTED, "bd_forward: pnp mode not built");
+  if (e->graphs_on && !e->profile && B * T <= e->graph_max_views) {
+    // small shapes are launch-bound: stage the inputs into the engine's own buffers (device-to-device, a few MB) and replay
+    // the captured launch chain; the results are copied out of the workspace afterwards
+    int r = ensure_staging(e);
+    if (r != BD_OK) return r;
+    const size_t es = in_dtype == BD_BF16 ? 2 : 4, SS = static_cast<size_t>(e->S) * e->S, L = static_cast<size_t>(B) * T;
+    CK(cudaMemcpyAsync(e->in_images, images, L * 3 * SS * es, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(e->in_bbox, bbox_feat, L * 8 * SS * es, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(e->qidx, query_idx, static_cast<size_t>(B) * 8, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(e->bbox3d_q, bbox3d_q, static_cast<size_t>(B) * 24 * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(e->K_q, K_q, static_cast<size_t>(B) * 9 * 4, cudaMemcpyDeviceToDevice, s));
+    r = graph_run(e, graph_key(2, in_dtype, B, T, po), s, [&](cudaStream_t st) {
+      const int q = encoder_body(e, in_dtype, 0, B * T, st);
+      return q != BD_OK ? q : decoder_post_body(e, in_dtype, B, T, po, st);
+    });
+    if (r != BD_OK) return r;
+    CK(cudaMemcpyAsync(corners_px, e->corners_px, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(corners_norm, e->corners_norm, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(poses_out, e->poses, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToDevice, s));
+    if (heat_out) CK(cudaMemcpyAsync(heat_out, e->heat, static_cast<size_t>(B) * 8 * SS * 4, cudaMemcpyDeviceToDevice, s));
+    return BD_OK;
+  }
   float* heat = heat_out ? heat_out : e->heat;
   int r = dino_forward_impl(e, images, in_dtype, e->tc ? nullptr : e->feats, B * T, s);
   if (r != BD_OK) return r;
   r = decoder_forward_impl(e, bbox_feat, in_dtype, e->feats, e->tc, query_idx, heat, nullptr, B, T, s);
   if (r != BD_OK) return r;
   LAUNCH(BD_PROF_TOPK, 1, corners_topk(heat, corners_px, corners_norm, nullptr, B, 8, e->S, s));
-  const PnpOpts po = to_opts(opts);
-  if (po.mode != 0 && po.mode != 1) return fail(BD_ERR_UNSUPPORTED, "bd_forward: pnp mode not built");
   LAUNCH(BD_PROF_PNP, 1, pnp_solve(corners_px, bbox3d_q, K_q, poses_out, po, B, 8, s));
   return BD_OK;
 }
@@ -553,12 +657,11 @@ static int forward_host_impl(bd_handle e, const void* images_host, const void* b
   if (B <= 0 || T <= 0 || B > e->Bmax || T > e->Tmax) return fail(BD_ERR_INVALID, "bd_forward_host: B/T exceed the workspace");
   const size_t es = in_dtype == BD_BF16 ? 2 : 4;
   const size_t SS = static_cast<size_t>(e->S) * e->S;
-  if (!e->in_images) {
-    const size_t Lm = e->Lmax;
-    DALLOC(e->in_images, Lm * 3 * SS * 4);
-    DALLOC(e->in_bbox, Lm * 8 * SS * 4);
-    CK(cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking));
+  {
+    int r = ensure_staging(e);
+    if (r != BD_OK) return r;
   }
+  if (!e->host_stream) CK(cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking));
   cudaStream_t s = e->host_stream;
   if (!e->copy_stream) {
     CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
@@ -602,17 +705,17 @@ static int forward_host_impl(bd_handle e, const void* images_host, const void* b
     const int b0 = b0s[c], nb = b0s[c + 1] - b0s[c];
     CK(cudaStreamWaitEvent(s, e->copy_ev[c], 0));
     if (nb <= 0) continue;
-    int r = dino_forward_impl(e, static_cast<char*>(e->in_images) + b0 * img_q, in_dtype, e->tc ? nullptr : e->feats, nb * T, s, b0 * T);
+    const PnpOpts none{};
+    int r = graph_run(e, graph_key(0, in_dtype, b0 * T, nb * T, none), s,
+                      [&](cudaStream_t st) { return encoder_body(e, in_dtype, b0 * T, nb * T, st); });
     if (r != BD_OK) return r;
   }
   CK(cudaStreamWaitEvent(s, e->copy_ev[7], 0));
   {
-    int r = decoder_forward_impl(e, e->in_bbox, in_dtype, e->feats, e->tc, e->qidx, e->heat, nullptr, B, T, s);
-    if (r != BD_OK) return r;
-    LAUNCH(BD_PROF_TOPK, 1, corners_topk(e->heat, e->corners_px, e->corners_norm, nullptr, B, 8, e->S, s));
     const PnpOpts po = to_opts(opts);
     if (po.mode != 0 && po.mode != 1) return fail(BD_ERR_UNSUPPORTED, "bd_forward_host: pnp mode not built");
-    LAUNCH(BD_PROF_PNP, 1, pnp_solve(e->corners_px, e->bbox3d_q, e->K_q, e->poses, po, B, 8, s));
+    int r = graph_run(e, graph_key(1, in_dtype, B, T, po), s, [&](cudaStream_t st) { return decoder_post_body(e, in_dtype, B, T, po, st); });
+    if (r != BD_OK) return r;
   }
   CK(cudaMemcpyAsync(corners_px_host, e->corners_px, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(corners_norm_host, e->corners_norm, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToHost, s));

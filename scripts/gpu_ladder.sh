@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > gpurun_out/ladder_gpu.txt 2>&1
 NODES="$@"
 if [ -z "$NODES" ]; then
-  NODES="tests/test_gpu_simt.py tests/test_gpu_tc.py::test_gemm_tc_f32 tests/test_gpu_tc.py::test_gemm_tc_epilogues tests/test_gpu_tc.py::test_qkv_project_tc tests/test_gpu_tc.py::test_attention_tc_pingpong tests/test_gpu_forward.py tests/test_gpu_dense.py tests/test_metrics.py tests/test_checkpoint.py"
+  NODES="tests/test_gpu_simt.py tests/test_gpu_tc.py::test_gemm_tc_f32 tests/test_gpu_tc.py::test_gemm_tc_epilogues tests/test_gpu_tc.py::test_qkv_project_tc tests/test_gpu_tc.py::test_attention_tc_pingpong tests/test_gpu_forward.py tests/test_gpu_bf16_parity.py tests/test_gpu_dense.py tests/test_metrics.py tests/test_checkpoint.py"
 fi
 i=0
 for n in $NODES; do

@@ -244,3 +244,49 @@ def test_reference_feature_cache_equals_full_forward(weights):
     assert torch.equal(out["pred_bbox"], ref["pred_bbox"][mask])
     assert torch.equal(out["regression_boxes"], ref["regression_boxes"][mask])
     assert torch.equal(out["pred_poses"], ref["pred_poses"][mask])
+
+
+@pytest.mark.parametrize("precision,dtype", [("exact", torch.float32), ("bf16", torch.bfloat16)])
+def test_graph_replay_equals_eager_launches(weights, monkeypatch, precision, dtype):
+    """bd_forward at small shapes stages its inputs and replays a captured CUDA graph of the launch chain (call 1 eager,
+    call 2 captured, call 3+ replayed): every call must return bit-identical results, equal to an engine created with
+    BOXDREAMER_B200_GRAPHS=0, also for fresh inputs (the replay must read the staged inputs, not captured pointers), on a
+    non-default stream, and through the host-buffer entry (per-stage graphs)."""
+    B, T = 2, 3
+    def inputs(seed):
+        data = synth.synth_inputs(B, T, 224, seed=seed)
+        d = _to_cuda({k: (v.to(dtype) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in data.items()})
+        mask = torch.zeros(B, T, dtype=torch.bool)
+        mask[torch.arange(B), data["query_idx"]] = True
+        return (d["images"].contiguous(), d["bbox_feat"].contiguous(), d["query_idx"],
+                data["bbox_3d"][mask].float().cuda().contiguous(), data["non_ndc_intrinsics"][mask].float().cuda().contiguous())
+    monkeypatch.setenv("BOXDREAMER_B200_GRAPHS", "0")
+    m0 = _model(weights, precision)
+    a, b = inputs(91), inputs(92)
+    eng0 = m0._engine_for(a[0], B, T)
+    ref_a = [t.clone() for t in eng0.forward(*a)]
+    ref_b = [t.clone() for t in eng0.forward(*b)]
+    monkeypatch.setenv("BOXDREAMER_B200_GRAPHS", "1")
+    m1 = _model(weights, precision)
+    eng1 = m1._engine_for(a[0], B, T)
+    assert eng1.handle.value != eng0.handle.value
+    l0 = eng1.lib.bd_launch_count(eng1.handle)
+    for i, (x, ref) in enumerate([(a, ref_a), (a, ref_a), (a, ref_a), (b, ref_b), (a, ref_a)]):
+        got = eng1.forward(*x)
+        torch.cuda.synchronize()
+        for g, r, nm in zip(got, ref, ("heat", "corners_px", "corners_norm", "poses")):
+            assert torch.equal(g, r), f"call {i}: {nm} differs between graph replay and eager launches"
+    per_call = (eng1.lib.bd_launch_count(eng1.handle) - l0) / 5
+    assert per_call > 100, "replayed launches are not counted"
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        got = eng1.forward(*b)
+    side.synchronize()
+    assert all(torch.equal(g, r) for g, r in zip(got, ref_b)), "graph replay on a side stream differs"
+    # host-buffer entry: encoder and decoder stages are replayed separately
+    host = [t.cpu().contiguous() for t in b]
+    for i in range(3):
+        got = eng1.forward_host(*host, want_heat=True)
+        for g, r, nm in zip(got, ref_b, ("heat", "corners_px", "corners_norm", "poses")):
+            assert torch.equal(g.cpu(), r.cpu()), f"host call {i}: {nm} differs"

@@ -8,7 +8,8 @@
 One step = one pass of the whole path (DINOv2 -> BETR -> heat maps -> top-20 corners -> PnP) over one batch of
 synthetic queries; the N=1 workload is BASELINE.json configs[1]: batch 64 queries x 5 reference views (T = 6),
 224 px, bf16.  Weak scaling: every rank processes its own 64-query shard (configs[2] at N = 8), weights arrive by one
-broadcast from rank 0, packed poses + corners are all-gathered every step (inside the timed region).
+broadcast from rank 0, the packed poses + corners records are all-gathered every step (one asynchronous NCCL call per step, waited on
+one step later, all inside the timed region).
 
 Printed JSON (one line, rank 0): see the contract in the task statement; extra keys `roofline` (attention kernel,
 in-step CUDA-event timing on the launching stream), `cpu_baseline` (the CPU oracle port on this box's host cores),
@@ -388,11 +389,30 @@ def run_ours(args, rank, world, local_rank):
     lib = eng.lib
     counts = [B] * world
 
+    # N > 1: the PnP kernel writes the packed [B, 28] record itself and the step ends with ONE NCCL all-gather of it (no packing /
+    # padding / re-assembly kernels).  The gather is asynchronous and double-buffered: it is waited on one step later, so it
+    # overlaps the next step's encoder and no rank waits for the slowest GPU inside a step.
+    recs = [torch.empty(B, bdist.RECORD, device=dev) for _ in range(2)] if world > 1 else None
+    outs = [torch.empty(world * B, bdist.RECORD, device=dev) for _ in range(2)] if world > 1 else None
+    pending = [None, None]
+    step_no = [0]
+
     def step():
-        heat, px, nm, poses = eng.forward(d_images, d_bbox, d_qidx, d_X, d_K, want_heat=False)
-        if world > 1:
-            return bdist.all_gather_results(bdist.pack_results(poses, nm), counts)
-        return poses
+        if world == 1:
+            return eng.forward(d_images, d_bbox, d_qidx, d_X, d_K, want_heat=False)[3]
+        k = step_no[0] & 1
+        step_no[0] += 1
+        if pending[k] is not None:      # the gather that used these buffers two steps ago
+            pending[k].wait()
+        eng.forward_packed(d_images, d_bbox, d_qidx, d_X, d_K, out=recs[k])
+        _, pending[k] = bdist.gather_records(recs[k], out=outs[k], async_op=True)
+        return outs[k]
+
+    def drain():
+        for k in range(2):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
 
     def barrier():
         if world > 1:
@@ -401,6 +421,7 @@ def run_ours(args, rank, world, local_rank):
 
     for _ in range(max(args.warmup, 3)):
         step()
+    drain()
     barrier()
 
     # ---- timed region: K steps, CUDA events, clocks sampled during it ----
@@ -414,13 +435,22 @@ def run_ours(args, rank, world, local_rank):
     ev0.record()
     for _ in range(args.steps):
         step()
+    ev_own = torch.cuda.Event(enable_timing=True)
+    ev_own.record()                    # this rank's own K steps are enqueued up to here; the last gathers may still be waiting for peers
+    drain()                            # every gather has completed inside the timed region
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    ms_own = ev0.elapsed_time(ev_own)
     launches = lib.bd_launch_count(eng.handle) - launches0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    per_rank_ms = None
     if world > 1:
+        allms = torch.empty(world, 2, device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(allms, torch.tensor([[ms, ms_own]], device=dev, dtype=torch.float64))
+        per_rank_ms = [float(x) / args.steps for x in allms[:, 0].tolist()]
+        per_rank_own = [float(x) / args.steps for x in allms[:, 1].tolist()]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = world * B * args.steps / (ms / 1e3)
@@ -596,6 +626,13 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches), "kernel_ms_per_step": kernel_ms, "kernel_launches_per_step": kernel_n,
             "clocks": clocks, "flops_per_query": fl["total"],
         }
+        if per_rank_ms is not None:
+            line["per_rank_ms_per_step"] = {"min": min(per_rank_ms), "max": max(per_rank_ms), "rank0": per_rank_ms[0], "all": per_rank_ms,
+                                            "own_work_before_last_gathers": per_rank_own,
+                                            "note": "`all` ends after the last gathers (which wait for the slowest rank); `own_work...` is each rank's K "
+                                                    "steps without that final wait: its spread is the GPU-to-GPU (power cap) spread"}
+            line["result_exchange"] = ("PnP kernel writes the packed [64, 28] record; one NCCL all-gather per step (async, double-buffered, waited "
+                                       "on one step later; all gathers complete inside the timed region)")
         print(json.dumps(line), flush=True)
     return 0
 

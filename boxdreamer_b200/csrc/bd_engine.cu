@@ -64,6 +64,7 @@ struct bd_engine {
   float* logits = nullptr;   // f32 [B*P, patch*patch*8]
   float* heat = nullptr;     // f32 [B,8,S,S]
   float* corners_px = nullptr; float* corners_norm = nullptr; float* poses = nullptr;
+  float* rec = nullptr;      // f32 [B, 28] packed result record {R|t, 8 normalised corners} (bd_forward_packed)
   float* bbox3d_q = nullptr; float* K_q = nullptr; int64_t* qidx = nullptr;
   void* in_images = nullptr; void* in_bbox = nullptr;  // device staging for bd_forward_host
   void* in_bbox_px = nullptr;                          // bd_forward_host_px: projected corners [Lmax,8,2] fp32
@@ -214,6 +215,7 @@ extern "C" int bd_create(bd_handle* out, const bd_config* cfg) {
   DALLOC(e->corners_px, static_cast<size_t>(e->Bmax) * 16 * 4);
   DALLOC(e->corners_norm, static_cast<size_t>(e->Bmax) * 16 * 4);
   DALLOC(e->poses, static_cast<size_t>(e->Bmax) * 16 * 4);
+  DALLOC(e->rec, static_cast<size_t>(e->Bmax) * 28 * 4);
   DALLOC(e->bbox3d_q, static_cast<size_t>(e->Bmax) * 24 * 4);
   DALLOC(e->K_q, static_cast<size_t>(e->Bmax) * 9 * 4);
   DALLOC(e->qidx, static_cast<size_t>(e->Bmax) * 8);
@@ -561,7 +563,7 @@ static int decoder_post_body(bd_engine* e, int dtype, int B, int T, const PnpOpt
   int r = decoder_forward_impl(e, e->in_bbox, dtype, e->feats, e->tc, e->qidx, e->heat, nullptr, B, T, s);
   if (r != BD_OK) return r;
   LAUNCH(BD_PROF_TOPK, 1, corners_topk(e->heat, e->corners_px, e->corners_norm, nullptr, B, 8, e->S, s));
-  LAUNCH(BD_PROF_PNP, 1, pnp_solve(e->corners_px, e->bbox3d_q, e->K_q, e->poses, po, B, 8, s));
+  LAUNCH(BD_PROF_PNP, 1, pnp_solve(e->corners_px, e->bbox3d_q, e->K_q, e->poses, po, B, 8, s, po.mode == 0 ? e->rec : nullptr, e->corners_norm));
   return BD_OK;
 }
 static std::vector<long long> graph_key(int stage, int dtype, int a, int b, const PnpOpts& po) {
@@ -604,16 +606,17 @@ extern "C" int bd_pnp(bd_handle e, const float* corners_px, const float* bbox3d,
   return BD_OK;
 }
 
-extern "C" int bd_forward(bd_handle e, const void* images, const void* bbox_feat, int32_t in_dtype, const int64_t* query_idx,
-                          const float* bbox3d_q, const float* K_q, float* heat_out, float* corners_px, float* corners_norm,
-                          float* poses_out, const bd_pnp_opts* opts, int32_t B, int32_t T, void* stream) {
-  if (!e || !images || !bbox_feat || !query_idx || !bbox3d_q || !K_q || !corners_px || !corners_norm || !poses_out)
-    return fail(BD_ERR_INVALID, "bd_forward: null argument");
+// bd_forward / bd_forward_packed: device pointers in, device results out.  Null result pointers select the engine's own buffers;
+// rec_out (mode 0 only) receives the packed [B, 28] record written by the PnP kernel's epilogue.
+static int forward_device_impl(bd_handle e, const void* images, const void* bbox_feat, int32_t in_dtype, const int64_t* query_idx,
+                               const float* bbox3d_q, const float* K_q, float* heat_out, float* corners_px, float* corners_norm,
+                               float* poses_out, float* rec_out, const bd_pnp_opts* opts, int32_t B, int32_t T, void* stream) {
   DevGuard dev_guard(e);
   if (B <= 0 || T <= 0 || B > e->Bmax || T > e->Tmax) return fail(BD_ERR_INVALID, "bd_forward: B/T exceed the workspace");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const PnpOpts po = to_opts(opts);
   if (po.mode != 0 && po.mode != 1) return fail(BD_ERR_UNSUPPORTED, "bd_forward: pnp mode not built");
+  if (rec_out && po.mode != 0) return fail(BD_ERR_UNSUPPORTED, "bd_forward_packed: the packed record is written by the iterative PnP kernel (mode 0) only");
   if (e->graphs_on && !e->profile && B * T <= e->graph_max_views) {
     // small shapes are launch-bound: stage the inputs into the engine's own buffers (device-to-device, a few MB) and replay
     // the captured launch chain; the results are copied out of the workspace afterwards
@@ -630,20 +633,41 @@ extern "C" int bd_forward(bd_handle e, const void* images, const void* bbox_feat
       return q != BD_OK ? q : decoder_post_body(e, in_dtype, B, T, po, st);
     });
     if (r != BD_OK) return r;
-    CK(cudaMemcpyAsync(corners_px, e->corners_px, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(corners_norm, e->corners_norm, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(poses_out, e->poses, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToDevice, s));
+    if (corners_px) CK(cudaMemcpyAsync(corners_px, e->corners_px, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToDevice, s));
+    if (corners_norm) CK(cudaMemcpyAsync(corners_norm, e->corners_norm, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToDevice, s));
+    if (poses_out) CK(cudaMemcpyAsync(poses_out, e->poses, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToDevice, s));
+    if (rec_out) CK(cudaMemcpyAsync(rec_out, e->rec, static_cast<size_t>(B) * 28 * 4, cudaMemcpyDeviceToDevice, s));
     if (heat_out) CK(cudaMemcpyAsync(heat_out, e->heat, static_cast<size_t>(B) * 8 * SS * 4, cudaMemcpyDeviceToDevice, s));
     return BD_OK;
   }
   float* heat = heat_out ? heat_out : e->heat;
+  if (!corners_px) corners_px = e->corners_px;
+  if (!corners_norm) corners_norm = e->corners_norm;
+  if (!poses_out) poses_out = e->poses;
   int r = dino_forward_impl(e, images, in_dtype, e->tc ? nullptr : e->feats, B * T, s);
   if (r != BD_OK) return r;
   r = decoder_forward_impl(e, bbox_feat, in_dtype, e->feats, e->tc, query_idx, heat, nullptr, B, T, s);
   if (r != BD_OK) return r;
   LAUNCH(BD_PROF_TOPK, 1, corners_topk(heat, corners_px, corners_norm, nullptr, B, 8, e->S, s));
-  LAUNCH(BD_PROF_PNP, 1, pnp_solve(corners_px, bbox3d_q, K_q, poses_out, po, B, 8, s));
+  LAUNCH(BD_PROF_PNP, 1, pnp_solve(corners_px, bbox3d_q, K_q, poses_out, po, B, 8, s, rec_out, corners_norm));
   return BD_OK;
+}
+
+extern "C" int bd_forward(bd_handle e, const void* images, const void* bbox_feat, int32_t in_dtype, const int64_t* query_idx,
+                          const float* bbox3d_q, const float* K_q, float* heat_out, float* corners_px, float* corners_norm,
+                          float* poses_out, const bd_pnp_opts* opts, int32_t B, int32_t T, void* stream) {
+  if (!e || !images || !bbox_feat || !query_idx || !bbox3d_q || !K_q || !corners_px || !corners_norm || !poses_out)
+    return fail(BD_ERR_INVALID, "bd_forward: null argument");
+  return forward_device_impl(e, images, bbox_feat, in_dtype, query_idx, bbox3d_q, K_q, heat_out, corners_px, corners_norm, poses_out,
+                             nullptr, opts, B, T, stream);
+}
+
+extern "C" int bd_forward_packed(bd_handle e, const void* images, const void* bbox_feat, int32_t in_dtype, const int64_t* query_idx,
+                                 const float* bbox3d_q, const float* K_q, float* rec_out, const bd_pnp_opts* opts, int32_t B, int32_t T,
+                                 void* stream) {
+  if (!e || !images || !bbox_feat || !query_idx || !bbox3d_q || !K_q || !rec_out) return fail(BD_ERR_INVALID, "bd_forward_packed: null argument");
+  return forward_device_impl(e, images, bbox_feat, in_dtype, query_idx, bbox3d_q, K_q, nullptr, nullptr, nullptr, nullptr, rec_out, opts,
+                             B, T, stream);
 }
 
 static int forward_host_impl(bd_handle e, const void* images_host, const void* bbox_feat_host, const float* bbox_px_host,

@@ -1186,7 +1186,7 @@ cudaError_t pnp_solve(const float* corners_px, const float* bbox3d, const float*
     return cudaGetLastError();
   }
   static const bool thread_kernel = getenv("BD_PNP_THREAD") != nullptr;   // debug switch: the thread-per-query kernel
-  if (n_pts <= PW_MAXPTS && !thread_kernel) {
+  if (n_pts <= PW_MAXPTS && (!thread_kernel || rec != nullptr)) {
     pnp_iterative_warp_kernel<<<(B + PW_WARPS - 1) / PW_WARPS, PW_WARPS * 32, 0, s>>>(corners_px, bbox3d, K, poses, rec, corners_norm, B, n_pts,
                                                                                     max_iter);
     return cudaGetLastError();

@@ -84,6 +84,18 @@ def unpack_results(rec: torch.Tensor):
     return poses, rec[:, 12:].view(B, 8, 2)
 
 
+def gather_records(rec_local: torch.Tensor, out: torch.Tensor | None = None, group=None, async_op: bool = False):
+    """Equal shards (every rank holds [B, 28], as Engine.forward_packed writes it): ONE collective into `out`
+    [world * B, 28] in rank order, nothing else on the stream -- no packing, padding or re-assembly kernels.  With
+    async_op=True the returned work handle is waited on when the records are consumed, so the gather of step k overlaps
+    the encoder of step k + 1 (use alternating `rec_local` / `out` buffers).  Returns (out, work | None)."""
+    world = dist.get_world_size(group)
+    if out is None:
+        out = torch.empty(world * rec_local.shape[0], rec_local.shape[1], dtype=rec_local.dtype, device=rec_local.device)
+    work = dist.all_gather_into_tensor(out, rec_local, group=group, async_op=async_op)
+    return out, (work if async_op else None)
+
+
 def all_gather_results(rec_local: torch.Tensor, counts, group=None) -> torch.Tensor:
     """All-gather of ragged shards: every rank returns [sum(counts), 28] in rank order."""
     world = dist.get_world_size(group)

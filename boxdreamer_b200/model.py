@@ -185,6 +185,18 @@ class Engine:
         return heat, px, nm, poses
 
     @_on_device
+    def forward_packed(self, images, bbox_feat, query_idx, bbox3d_q, K_q, out=None, opts=None):
+        """The forward, returning the packed [B, 28] result record (dist.RECORD: R|t, normalised corners) written by the PnP
+        kernel itself -- the payload of the multi-GPU result gather (dist.gather_records)."""
+        B, T = images.shape[:2]
+        rec = out if out is not None else torch.empty(B, 28, device=images.device, dtype=torch.float32)
+        o = C.byref(opts) if opts is not None else None
+        _lib.check(self.lib.bd_forward_packed(self.handle, _lib.ptr(images), _lib.ptr(bbox_feat), self._dt(images),
+                                              _lib.ptr(query_idx), _lib.ptr(bbox3d_q), _lib.ptr(K_q), _lib.ptr(rec), o, B, T,
+                                              _lib.stream_ptr()), "bd_forward_packed")
+        return rec
+
+    @_on_device
     def forward_host(self, images, bbox_feat, query_idx, bbox3d_q, K_q, want_heat=False, opts=None):
         """Host tensors in, host tensors out (H2D/D2H inside the call)."""
         B, T = images.shape[:2]

@@ -109,10 +109,20 @@ int bd_pnp(bd_handle h, const float* corners_px, const float* bbox3d, const floa
 /* BoxDreamer.forward (BoxDreamerModel.py:112-191), eval, bb8/heatmap: the whole path on `stream`.
  * images [B,T,3,S,S], bbox_feat [B,T,8,S,S] (same dtype), query_idx [B], bbox3d_q [B,8,3], K_q [B,3,3]
  * (query rows, fp32) -> heat_out [B,8,S,S], corners_px/norm [B,8,2], poses_out [B,4,4].
- * heat_out may be NULL (an internal buffer is used). */
+ * heat_out may be NULL (an internal buffer is used).
+ * Shapes of at most BOXDREAMER_B200_GRAPH_MAX_VIEWS (default 24) views are launch-bound: their inputs are staged into the
+ * handle's buffers and the ~220 launches are replayed as one CUDA graph (BOXDREAMER_B200_GRAPHS=0: always launch eagerly). */
 int bd_forward(bd_handle h, const void* images, const void* bbox_feat, int32_t in_dtype, const int64_t* query_idx,
                const float* bbox3d_q, const float* K_q, float* heat_out, float* corners_px, float* corners_norm,
                float* poses_out, const bd_pnp_opts* opts, int32_t B, int32_t T, void* stream);
+
+/* The same forward, returning only what a multi-GPU evaluation exchanges: rec_out [B,28] fp32 = {R|t (12, row-major 3x4),
+ * 8 normalised corners (16)} per query, written by the PnP kernel's epilogue (no packing pass).  It is the payload of the
+ * per-step result all-gather that replaces the pickled all_gather of src/utils/comm.py:179-219 (boxdreamer_b200/dist.py).
+ * Iterative PnP (opts->mode 0) only. */
+int bd_forward_packed(bd_handle h, const void* images, const void* bbox_feat, int32_t in_dtype, const int64_t* query_idx,
+                      const float* bbox3d_q, const float* K_q, float* rec_out, const bd_pnp_opts* opts, int32_t B, int32_t T,
+                      void* stream);
 
 /* Same, with HOST buffers (pinned or pageable): stages H2D, runs, copies corners + poses (and the heat maps
  * when heat_out_host != NULL) back and synchronises.  This is what a ctypes/cgo/JNI caller without device

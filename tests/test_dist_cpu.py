@@ -45,7 +45,19 @@ def _worker(rank, world, port, ret):
         allrec = bdist.all_gather_results(rec, counts)
         P, Cn = bdist.unpack_results(allrec)
         ok_g = allrec.shape == (5, bdist.RECORD) and torch.allclose(P, poses) and torch.allclose(Cn, corners)
-        ret[rank] = (ok_w, ok_s, ok_g)
+        # (4) equal shards: one collective, double-buffered, waited on one step later (what bench.py --gpus N does)
+        recs = [torch.full((3, bdist.RECORD), float(10 * rank + k)) for k in range(2)]
+        outs, works = [None, None], [None, None]
+        for k in range(2):
+            outs[k], works[k] = bdist.gather_records(recs[k], async_op=True)
+        ok_e = True
+        for k in range(2):
+            works[k].wait()
+            want = torch.cat([torch.full((3, bdist.RECORD), float(10 * r + k)) for r in range(world)])
+            ok_e = ok_e and torch.equal(outs[k], want)
+        sync_out, none = bdist.gather_records(recs[0])
+        ok_e = ok_e and none is None and torch.equal(sync_out, outs[0])
+        ret[rank] = (ok_w, ok_s, ok_g and ok_e)
     finally:
         dist.destroy_process_group()
 

@@ -290,3 +290,26 @@ def test_graph_replay_equals_eager_launches(weights, monkeypatch, precision, dty
         got = eng1.forward_host(*host, want_heat=True)
         for g, r, nm in zip(got, ref_b, ("heat", "corners_px", "corners_norm", "poses")):
             assert torch.equal(g.cpu(), r.cpu()), f"host call {i}: {nm} differs"
+
+
+@pytest.mark.parametrize("B,T", [(2, 3), (5, 6)])
+def test_forward_packed_record_equals_packed_forward(weights, B, T):
+    """bd_forward_packed: the [B, 28] record written by the PnP kernel's epilogue equals dist.pack_results of bd_forward's
+    poses and normalised corners (staged / graph-replayed shape and eagerly launched shape)."""
+    from boxdreamer_b200 import dist as bdist
+    m = _model(weights, "bf16")
+    data = synth.synth_inputs(B, T, 224, seed=77)
+    d = _to_cuda({k: (v.to(torch.bfloat16) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in data.items()})
+    mask = torch.zeros(B, T, dtype=torch.bool)
+    mask[torch.arange(B), data["query_idx"]] = True
+    X = data["bbox_3d"][mask].float().cuda().contiguous()
+    K = data["non_ndc_intrinsics"][mask].float().cuda().contiguous()
+    eng = m._engine_for(d["images"], B, T)
+    args = (d["images"].contiguous(), d["bbox_feat"].contiguous(), d["query_idx"], X, K)
+    for _ in range(3):   # eager, captured, replayed (small shape)
+        _, _, nm, poses = eng.forward(*args, want_heat=False)
+        rec = eng.forward_packed(*args)
+        torch.cuda.synchronize()
+        assert torch.equal(rec, bdist.pack_results(poses, nm))
+        P, Cn = bdist.unpack_results(rec)
+        assert torch.equal(P[:, :3], poses[:, :3]) and torch.equal(Cn, nm)

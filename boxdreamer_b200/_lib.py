@@ -19,7 +19,7 @@ PROF_CATS = ["gemm_qkv", "attention", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm
 # every symbol include/boxdreamer_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "bd_last_error", "bd_version", "bd_create", "bd_destroy", "bd_load_weight", "bd_finalize_weights",
-    "bd_dino_forward", "bd_decoder_forward", "bd_corners_topk", "bd_pnp", "bd_forward", "bd_forward_packed", "bd_forward_host",
+    "bd_dino_forward", "bd_decoder_forward", "bd_corners_topk", "bd_pnp", "bd_forward", "bd_forward_packed", "bd_forward_host", "bd_forward_host_submit", "bd_forward_host_wait",
     "bd_make_bbox_features", "bd_forward_host_px", "bd_pose_metrics",
     "bd_gemm", "bd_qkv_project", "bd_attention", "bd_layernorm", "bd_launch_count", "bd_profile_enable", "bd_profile_read", "bd_debug_attention_trace",
 ]
@@ -70,6 +70,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.bd_corners_topk.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
     lib.bd_pnp.argtypes = [vp, vp, vp, vp, vp, C.POINTER(BdPnpOpts), i32, i32, vp]
     lib.bd_forward.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(BdPnpOpts), i32, i32, vp]
+    lib.bd_forward_host_submit.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(BdPnpOpts), i32, i32]
+    lib.bd_forward_host_wait.argtypes = [vp, i32]
     lib.bd_forward_packed.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(BdPnpOpts), i32, i32, vp]
     lib.bd_forward_host.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(BdPnpOpts), i32, i32]
     lib.bd_forward_host_px.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(BdPnpOpts), i32, i32]

@@ -66,12 +66,18 @@ struct bd_engine {
   float* corners_px = nullptr; float* corners_norm = nullptr; float* poses = nullptr;
   float* rec = nullptr;      // f32 [B, 28] packed result record {R|t, 8 normalised corners} (bd_forward_packed)
   float* bbox3d_q = nullptr; float* K_q = nullptr; int64_t* qidx = nullptr;
-  void* in_images = nullptr; void* in_bbox = nullptr;  // device staging for bd_forward_host
-  void* in_bbox_px = nullptr;                          // bd_forward_host_px: projected corners [Lmax,8,2] fp32
+  // Input staging: two slots, so that bd_forward_host_submit can copy the next batch in while the previous one computes
+  // (slot 0 also stages the graph-replayed shapes of bd_forward).  in_bbox_px: projected corners [Lmax,8,2] fp32 (_px entries).
+  struct HostSlot {
+    void* in_images = nullptr; void* in_bbox = nullptr; void* in_bbox_px = nullptr;
+    cudaEvent_t copy_ev[8] = {nullptr};
+    cudaEvent_t done = nullptr;
+    bool pending = false;          // submitted, not yet waited for
+  };
+  HostSlot slot[2];
   float* pos_dec = nullptr;  // f32 [P, d] 2-D sincos table
   cudaStream_t host_stream = nullptr;
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t copy_ev[8] = {nullptr};
   // CUDA graphs of the launch chain (graph_run): one executable per (stage, shape, options), captured on `cap_stream`
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int calls = 0; bool unusable = false; long long launches = 0; };
   std::map<std::vector<long long>, GraphEntry> graphs;
@@ -234,7 +240,10 @@ extern "C" int bd_destroy(bd_handle e) {
   for (void* p : e->allocs) cudaFree(p);
   if (e->host_stream) cudaStreamDestroy(e->host_stream);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
-  for (int i = 0; i < 8; ++i) if (e->copy_ev[i]) cudaEventDestroy(e->copy_ev[i]);
+  for (auto& sl : e->slot) {
+    for (int i = 0; i < 8; ++i) if (sl.copy_ev[i]) cudaEventDestroy(sl.copy_ev[i]);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
   drop_graphs(e);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   delete e;
@@ -545,31 +554,32 @@ static PnpOpts to_opts(const bd_pnp_opts* o) {
   return p;
 }
 
-static int ensure_staging(bd_engine* e) {
-  if (e->in_images) return BD_OK;
+static int ensure_staging(bd_engine* e, int k) {
+  bd_engine::HostSlot& sl = e->slot[k];
+  if (sl.in_images) return BD_OK;
   const size_t SS = static_cast<size_t>(e->S) * e->S, Lm = e->Lmax;
-  DALLOC(e->in_images, Lm * 3 * SS * 4);
-  DALLOC(e->in_bbox, Lm * 8 * SS * 4);
+  DALLOC(sl.in_images, Lm * 3 * SS * 4);
+  DALLOC(sl.in_bbox, Lm * 8 * SS * 4);
   return BD_OK;
 }
 
 // The two stages of a forward on the engine-owned staging buffers (in_images / in_bbox / qidx / bbox3d_q / K_q -> heat,
 // corners_px, corners_norm, poses): the encoder over images [img0, img0 + L), and decoder + corner extraction + PnP.
-static int encoder_body(bd_engine* e, int dtype, int img0, int L, cudaStream_t s) {
+static int encoder_body(bd_engine* e, int k, int dtype, int img0, int L, cudaStream_t s) {
   const size_t img_b = static_cast<size_t>(3) * e->S * e->S * (dtype == BD_BF16 ? 2 : 4);
-  return dino_forward_impl(e, static_cast<char*>(e->in_images) + img0 * img_b, dtype, e->tc ? nullptr : e->feats, L, s, img0);
+  return dino_forward_impl(e, static_cast<char*>(e->slot[k].in_images) + img0 * img_b, dtype, e->tc ? nullptr : e->feats, L, s, img0);
 }
-static int decoder_post_body(bd_engine* e, int dtype, int B, int T, const PnpOpts& po, cudaStream_t s) {
-  int r = decoder_forward_impl(e, e->in_bbox, dtype, e->feats, e->tc, e->qidx, e->heat, nullptr, B, T, s);
+static int decoder_post_body(bd_engine* e, int k, int dtype, int B, int T, const PnpOpts& po, cudaStream_t s) {
+  int r = decoder_forward_impl(e, e->slot[k].in_bbox, dtype, e->feats, e->tc, e->qidx, e->heat, nullptr, B, T, s);
   if (r != BD_OK) return r;
   LAUNCH(BD_PROF_TOPK, 1, corners_topk(e->heat, e->corners_px, e->corners_norm, nullptr, B, 8, e->S, s));
   LAUNCH(BD_PROF_PNP, 1, pnp_solve(e->corners_px, e->bbox3d_q, e->K_q, e->poses, po, B, 8, s, po.mode == 0 ? e->rec : nullptr, e->corners_norm));
   return BD_OK;
 }
-static std::vector<long long> graph_key(int stage, int dtype, int a, int b, const PnpOpts& po) {
+static std::vector<long long> graph_key(int stage, int slot, int dtype, int a, int b, const PnpOpts& po) {
   long long thr_bits = 0;
   memcpy(&thr_bits, &po.thr_px, sizeof(float));
-  return {stage, dtype, a, b, po.mode, po.n_hyp, thr_bits, po.seed, po.max_iter};
+  return {stage, slot, dtype, a, b, po.mode, po.n_hyp, thr_bits, po.seed, po.max_iter};
 }
 
 extern "C" int bd_dino_forward(bd_handle e, const void* images, int32_t dtype, float* feats_out, int32_t L, void* stream) {
@@ -620,17 +630,20 @@ static int forward_device_impl(bd_handle e, const void* images, const void* bbox
   if (e->graphs_on && !e->profile && B * T <= e->graph_max_views) {
     // small shapes are launch-bound: stage the inputs into the engine's own buffers (device-to-device, a few MB) and replay
     // the captured launch chain; the results are copied out of the workspace afterwards
-    int r = ensure_staging(e);
+    int r = ensure_staging(e, 0);
     if (r != BD_OK) return r;
+    if (e->slot[0].pending) {   // a submitted host batch still owns slot 0: let it finish before its staging is overwritten
+      CK(cudaEventSynchronize(e->slot[0].done));
+    }
     const size_t es = in_dtype == BD_BF16 ? 2 : 4, SS = static_cast<size_t>(e->S) * e->S, L = static_cast<size_t>(B) * T;
-    CK(cudaMemcpyAsync(e->in_images, images, L * 3 * SS * es, cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(e->in_bbox, bbox_feat, L * 8 * SS * es, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(e->slot[0].in_images, images, L * 3 * SS * es, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(e->slot[0].in_bbox, bbox_feat, L * 8 * SS * es, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(e->qidx, query_idx, static_cast<size_t>(B) * 8, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(e->bbox3d_q, bbox3d_q, static_cast<size_t>(B) * 24 * 4, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(e->K_q, K_q, static_cast<size_t>(B) * 9 * 4, cudaMemcpyDeviceToDevice, s));
-    r = graph_run(e, graph_key(2, in_dtype, B, T, po), s, [&](cudaStream_t st) {
-      const int q = encoder_body(e, in_dtype, 0, B * T, st);
-      return q != BD_OK ? q : decoder_post_body(e, in_dtype, B, T, po, st);
+    r = graph_run(e, graph_key(2, 0, in_dtype, B, T, po), s, [&](cudaStream_t st) {
+      const int q = encoder_body(e, 0, in_dtype, 0, B * T, st);
+      return q != BD_OK ? q : decoder_post_body(e, 0, in_dtype, B, T, po, st);
     });
     if (r != BD_OK) return r;
     if (corners_px) CK(cudaMemcpyAsync(corners_px, e->corners_px, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToDevice, s));
@@ -670,32 +683,52 @@ extern "C" int bd_forward_packed(bd_handle e, const void* images, const void* bb
                              B, T, stream);
 }
 
-static int forward_host_impl(bd_handle e, const void* images_host, const void* bbox_feat_host, const float* bbox_px_host,
-                             int32_t in_dtype, const int64_t* query_idx_host, const float* bbox3d_q_host, const float* K_q_host,
-                             float* heat_out_host, float* corners_px_host, float* corners_norm_host, float* poses_out_host,
-                             const bd_pnp_opts* opts, int32_t B, int32_t T) {
+// Host-buffer entries.  submit: enqueue the H2D copies (copy stream), the forward (compute stream) and the D2H copies of the results
+// for staging slot k, return without waiting.  wait: block until slot k's results are in the host buffers given to submit.
+static int host_wait_impl(bd_handle e, int k) {
+  if (!e || k < 0 || k > 1) return fail(BD_ERR_INVALID, "bd_forward_host_wait: bad handle or slot");
+  bd_engine::HostSlot& sl = e->slot[k];
+  if (!sl.pending) return BD_OK;
+  DevGuard dev_guard(e);
+  sl.pending = false;
+  CK(cudaEventSynchronize(sl.done));
+  return BD_OK;
+}
+
+static int host_submit_impl(bd_handle e, int k, const void* images_host, const void* bbox_feat_host, const float* bbox_px_host,
+                            int32_t in_dtype, const int64_t* query_idx_host, const float* bbox3d_q_host, const float* K_q_host,
+                            float* heat_out_host, float* corners_px_host, float* corners_norm_host, float* poses_out_host,
+                            const bd_pnp_opts* opts, int32_t B, int32_t T) {
   if (!e || !images_host || (!bbox_feat_host && !bbox_px_host) || !query_idx_host || !bbox3d_q_host || !K_q_host || !corners_px_host ||
       !corners_norm_host || !poses_out_host)
     return fail(BD_ERR_INVALID, "bd_forward_host: null argument");
+  if (k < 0 || k > 1) return fail(BD_ERR_INVALID, "bd_forward_host_submit: slot must be 0 or 1");
   DevGuard dev_guard(e);
   if (B <= 0 || T <= 0 || B > e->Bmax || T > e->Tmax) return fail(BD_ERR_INVALID, "bd_forward_host: B/T exceed the workspace");
+  const PnpOpts po = to_opts(opts);
+  if (po.mode != 0 && po.mode != 1) return fail(BD_ERR_UNSUPPORTED, "bd_forward_host: pnp mode not built");
   const size_t es = in_dtype == BD_BF16 ? 2 : 4;
   const size_t SS = static_cast<size_t>(e->S) * e->S;
   {
-    int r = ensure_staging(e);
+    int r = host_wait_impl(e, k);   // a slot is reused only after its previous batch has been delivered
+    if (r != BD_OK) return r;
+    r = ensure_staging(e, k);
     if (r != BD_OK) return r;
   }
+  bd_engine::HostSlot& sl = e->slot[k];
   if (!e->host_stream) CK(cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking));
-  cudaStream_t s = e->host_stream;
-  if (!e->copy_stream) {
-    CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&e->copy_ev[i], cudaEventDisableTiming));
+  if (!e->copy_stream) CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  if (!sl.done) {
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&sl.copy_ev[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
   }
+  cudaStream_t s = e->host_stream;
   // Copy order = consumption order: the encoder only needs the images, so they go first; the reference heat maps (73 % of
   // the bytes) follow and land while the encoder runs.  The decoder, the corner extraction and PnP then see the whole batch
   // once.  The images can be split into `nchunk` pieces of whole queries (first one half-sized) so that the encoder starts
   // earlier, but at BASELINE config 2 the smaller encoder GEMMs cost more than the 2 ms of exposed transfer they hide
-  // (scripts/bench_e2e_chunks.py on B200: 1 chunk 49.3 ms, 2: 50.7, 3: 51.8, 4: 51.1) -- default 1.
+  // (scripts/bench_e2e_chunks.py on B200: 1 chunk 49.3 ms, 2: 50.7, 3: 51.8, 4: 51.1) -- default 1.  A caller that wants the
+  // transfer hidden completely alternates the two slots (submit k+1 before wait k).
   int nchunk = 1;
   if (const char* ev = getenv("BOXDREAMER_B200_HOST_CHUNKS")) nchunk = atoi(ev);
   if (nchunk < 1) nchunk = 1;
@@ -712,42 +745,60 @@ static int forward_host_impl(bd_handle e, const void* images_host, const void* b
   for (int c = 0; c < nchunk; ++c) {
     const int b0 = b0s[c], nb = b0s[c + 1] - b0s[c];
     if (nb > 0)
-      CK(cudaMemcpyAsync(static_cast<char*>(e->in_images) + b0 * img_q, static_cast<const char*>(images_host) + b0 * img_q, nb * img_q,
+      CK(cudaMemcpyAsync(static_cast<char*>(sl.in_images) + b0 * img_q, static_cast<const char*>(images_host) + b0 * img_q, nb * img_q,
                          cudaMemcpyHostToDevice, e->copy_stream));
-    CK(cudaEventRecord(e->copy_ev[c], e->copy_stream));
+    CK(cudaEventRecord(sl.copy_ev[c], e->copy_stream));
   }
   if (bbox_feat_host) {
-    CK(cudaMemcpyAsync(e->in_bbox, bbox_feat_host, B * box_q, cudaMemcpyHostToDevice, e->copy_stream));
+    CK(cudaMemcpyAsync(sl.in_bbox, bbox_feat_host, B * box_q, cudaMemcpyHostToDevice, e->copy_stream));
   } else {  // 64 bytes per view instead of the maps; rasterised on the device, on the copy stream (overlaps the encoder)
-    if (!e->in_bbox_px) DALLOC(e->in_bbox_px, static_cast<size_t>(e->Lmax) * 16 * 4);
-    CK(cudaMemcpyAsync(e->in_bbox_px, bbox_px_host, static_cast<size_t>(B) * T * 16 * 4, cudaMemcpyHostToDevice, e->copy_stream));
-    CK(bbox_heatmaps(reinterpret_cast<const float*>(e->in_bbox_px), e->in_bbox, in_dtype == BD_BF16, B * T, e->S, T, e->copy_stream));
+    if (!sl.in_bbox_px) DALLOC(sl.in_bbox_px, static_cast<size_t>(e->Lmax) * 16 * 4);
+    CK(cudaMemcpyAsync(sl.in_bbox_px, bbox_px_host, static_cast<size_t>(B) * T * 16 * 4, cudaMemcpyHostToDevice, e->copy_stream));
+    CK(bbox_heatmaps(reinterpret_cast<const float*>(sl.in_bbox_px), sl.in_bbox, in_dtype == BD_BF16, B * T, e->S, T, e->copy_stream));
     e->launches += 1;
   }
-  CK(cudaEventRecord(e->copy_ev[7], e->copy_stream));
+  CK(cudaEventRecord(sl.copy_ev[7], e->copy_stream));
   for (int c = 0; c < nchunk; ++c) {
     const int b0 = b0s[c], nb = b0s[c + 1] - b0s[c];
-    CK(cudaStreamWaitEvent(s, e->copy_ev[c], 0));
+    CK(cudaStreamWaitEvent(s, sl.copy_ev[c], 0));
     if (nb <= 0) continue;
     const PnpOpts none{};
-    int r = graph_run(e, graph_key(0, in_dtype, b0 * T, nb * T, none), s,
-                      [&](cudaStream_t st) { return encoder_body(e, in_dtype, b0 * T, nb * T, st); });
+    int r = graph_run(e, graph_key(0, k, in_dtype, b0 * T, nb * T, none), s,
+                      [&](cudaStream_t st) { return encoder_body(e, k, in_dtype, b0 * T, nb * T, st); });
     if (r != BD_OK) return r;
   }
-  CK(cudaStreamWaitEvent(s, e->copy_ev[7], 0));
+  CK(cudaStreamWaitEvent(s, sl.copy_ev[7], 0));
   {
-    const PnpOpts po = to_opts(opts);
-    if (po.mode != 0 && po.mode != 1) return fail(BD_ERR_UNSUPPORTED, "bd_forward_host: pnp mode not built");
-    int r = graph_run(e, graph_key(1, in_dtype, B, T, po), s, [&](cudaStream_t st) { return decoder_post_body(e, in_dtype, B, T, po, st); });
+    int r = graph_run(e, graph_key(1, k, in_dtype, B, T, po), s, [&](cudaStream_t st) { return decoder_post_body(e, k, in_dtype, B, T, po, st); });
     if (r != BD_OK) return r;
   }
   CK(cudaMemcpyAsync(corners_px_host, e->corners_px, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(corners_norm_host, e->corners_norm, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(poses_out_host, e->poses, static_cast<size_t>(B) * 16 * 4, cudaMemcpyDeviceToHost, s));
   if (heat_out_host) CK(cudaMemcpyAsync(heat_out_host, e->heat, static_cast<size_t>(B) * 8 * SS * 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  CK(cudaEventRecord(sl.done, s));
+  sl.pending = true;
   return BD_OK;
 }
+
+static int forward_host_impl(bd_handle e, const void* images_host, const void* bbox_feat_host, const float* bbox_px_host,
+                             int32_t in_dtype, const int64_t* query_idx_host, const float* bbox3d_q_host, const float* K_q_host,
+                             float* heat_out_host, float* corners_px_host, float* corners_norm_host, float* poses_out_host,
+                             const bd_pnp_opts* opts, int32_t B, int32_t T) {
+  int r = host_submit_impl(e, 0, images_host, bbox_feat_host, bbox_px_host, in_dtype, query_idx_host, bbox3d_q_host, K_q_host, heat_out_host,
+                           corners_px_host, corners_norm_host, poses_out_host, opts, B, T);
+  return r != BD_OK ? r : host_wait_impl(e, 0);
+}
+
+extern "C" int bd_forward_host_submit(bd_handle e, int32_t slot, const void* images_host, const void* bbox_feat_host,
+                                      const float* bbox_px_host, int32_t in_dtype, const int64_t* query_idx_host,
+                                      const float* bbox3d_q_host, const float* K_q_host, float* heat_out_host, float* corners_px_host,
+                                      float* corners_norm_host, float* poses_out_host, const bd_pnp_opts* opts, int32_t B, int32_t T) {
+  return host_submit_impl(e, slot, images_host, bbox_feat_host, bbox_px_host, in_dtype, query_idx_host, bbox3d_q_host, K_q_host,
+                          heat_out_host, corners_px_host, corners_norm_host, poses_out_host, opts, B, T);
+}
+
+extern "C" int bd_forward_host_wait(bd_handle e, int32_t slot) { return host_wait_impl(e, slot); }
 
 extern "C" int bd_forward_host(bd_handle e, const void* images_host, const void* bbox_feat_host, int32_t in_dtype,
                                const int64_t* query_idx_host, const float* bbox3d_q_host, const float* K_q_host,

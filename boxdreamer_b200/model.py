@@ -212,6 +212,30 @@ class Engine:
 
 
     @_on_device
+    def forward_host_submit(self, slot, images, bbox_feat, query_idx, bbox3d_q, K_q, bbox_px=None, want_heat=False, opts=None):
+        """Pipelined host entry: enqueue one batch on staging slot 0 / 1 and return the (pinned) result tensors, which are
+        filled once `forward_host_wait(slot)` returns.  Pass `bbox_px` [B,T,8,2] instead of `bbox_feat` (None) to have the
+        reference heat maps rasterised on the device.  The input tensors must stay alive until the wait."""
+        B, T = images.shape[:2]
+        heat = torch.empty(B, 8, self.S, self.S, dtype=torch.float32).pin_memory() if want_heat else None
+        px = torch.empty(B, 8, 2, dtype=torch.float32).pin_memory()
+        nm = torch.empty(B, 8, 2, dtype=torch.float32).pin_memory()
+        poses = torch.empty(B, 4, 4, dtype=torch.float32).pin_memory()
+        o = C.byref(opts) if opts is not None else None
+        _lib.check(self.lib.bd_forward_host_submit(self.handle, slot, _lib.ptr(images), _lib.ptr(bbox_feat), _lib.ptr(bbox_px),
+                                                   self._dt(images), _lib.ptr(query_idx), _lib.ptr(bbox3d_q), _lib.ptr(K_q),
+                                                   _lib.ptr(heat), _lib.ptr(px), _lib.ptr(nm), _lib.ptr(poses), o, B, T),
+                   "bd_forward_host_submit")
+        self._host_keepalive = getattr(self, "_host_keepalive", {})
+        self._host_keepalive[slot] = (images, bbox_feat, bbox_px, query_idx, bbox3d_q, K_q)
+        return heat, px, nm, poses
+
+    @_on_device
+    def forward_host_wait(self, slot):
+        _lib.check(self.lib.bd_forward_host_wait(self.handle, slot), "bd_forward_host_wait")
+        getattr(self, "_host_keepalive", {}).pop(slot, None)
+
+    @_on_device
     def forward_host_px(self, images, bbox_px, query_idx, bbox3d_q, K_q, want_heat=False, opts=None):
         """forward_host with the reference heat maps rasterised on the device from bbox_px [B,T,8,2] (host, fp32)."""
         B, T = images.shape[:2]

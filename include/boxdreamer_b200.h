@@ -132,6 +132,19 @@ int bd_forward_host(bd_handle h, const void* images_host, const void* bbox_feat_
                     float* corners_px_host, float* corners_norm_host, float* poses_out_host, const bd_pnp_opts* opts,
                     int32_t B, int32_t T);
 
+/* Pipelined form of the two host-buffer entries (bd_forward_host, and bd_forward_host_px below): `submit` enqueues the H2D
+ * copies, the forward and the D2H copies of the results for staging slot 0 or 1 and returns at once; `wait` blocks until that
+ * slot's results are in the host buffers passed to submit (which, like the inputs, must stay valid until then).  Alternating
+ * the two slots -- submit(k+1) before wait(k) -- hides the input transfer of the next batch behind the current batch's
+ * compute; this is the loop a data-loader thread of the reference (run.py / the Lightning predict loop) would drive.
+ * Exactly one of bbox_feat_host (maps, as bd_forward_host) and bbox_px_host (projected corners, as bd_forward_host_px) is
+ * non-NULL.  bd_forward_host(...) == submit(slot 0) + wait(slot 0). */
+int bd_forward_host_submit(bd_handle h, int32_t slot, const void* images_host, const void* bbox_feat_host,
+                           const float* bbox_px_host, int32_t in_dtype, const int64_t* query_idx_host, const float* bbox3d_q_host,
+                           const float* K_q_host, float* heat_out_host, float* corners_px_host, float* corners_norm_host,
+                           float* poses_out_host, const bd_pnp_opts* opts, int32_t B, int32_t T);
+int bd_forward_host_wait(bd_handle h, int32_t slot);
+
 /* ---- input synthesis on the device ---- */
 
 /* make_bbox_features(bbox, type="heatmap", shape=(S,S)) of the dataset (src/datasets/utils/base/bbox_utils.py:263-303):

@@ -313,3 +313,35 @@ def test_forward_packed_record_equals_packed_forward(weights, B, T):
         assert torch.equal(rec, bdist.pack_results(poses, nm))
         P, Cn = bdist.unpack_results(rec)
         assert torch.equal(P[:, :3], poses[:, :3]) and torch.equal(Cn, nm)
+
+
+def test_pipelined_host_entry_matches_blocking_call(weights):
+    """bd_forward_host_submit / _wait on alternating staging slots (batch k+1 submitted before batch k is waited for) returns,
+    for every batch, exactly what the blocking bd_forward_host returns -- for the map inputs and for the projected-corner
+    (_px) inputs, with different batches in flight at the same time."""
+    m = _model(weights, "bf16")
+    B, T = 2, 3
+    batches = []
+    for seed in (201, 202, 203, 204):
+        data = synth.synth_inputs(B, T, 224, seed=seed, dtype=torch.bfloat16)
+        mask = torch.zeros(B, T, dtype=torch.bool)
+        mask[torch.arange(B), data["query_idx"]] = True
+        batches.append((data["images"].contiguous().pin_memory(), data["bbox_feat"].contiguous().pin_memory(),
+                        data["query_idx"].contiguous(), data["bbox_3d"][mask].float().contiguous(),
+                        data["non_ndc_intrinsics"][mask].float().contiguous(),
+                        ((data["bbox_proj_crop"].float() + 1) / 2 * 224).contiguous()))
+    eng = m._engine_for(batches[0][0].cuda(), B, T)
+    for use_px in (False, True):
+        ref = []
+        for im, bb, qi, X, K, px in batches:
+            out = eng.forward_host_px(im, px, qi, X, K, want_heat=True) if use_px else eng.forward_host(im, bb, qi, X, K, want_heat=True)
+            ref.append([t.clone() for t in out])
+        for _ in range(2):   # second round: the per-slot stage graphs are replayed
+            got = [None] * len(batches)
+            for i, (im, bb, qi, X, K, px) in enumerate(batches):
+                got[i] = eng.forward_host_submit(i & 1, im, None if use_px else bb, qi, X, K, bbox_px=px if use_px else None, want_heat=True)
+                if i > 0:
+                    eng.forward_host_wait((i - 1) & 1)
+                    assert all(torch.equal(g, r) for g, r in zip(got[i - 1], ref[i - 1])), f"batch {i - 1} (px={use_px})"
+            eng.forward_host_wait((len(batches) - 1) & 1)
+            assert all(torch.equal(g, r) for g, r in zip(got[-1], ref[-1]))

@@ -55,8 +55,18 @@ def flops_per_query(T=T_VIEWS, P=256, d=768, dec_layers=12, dino_layers=12, n_to
     betr_att = dec_layers * 4 * N * N * d
     fusion = 2 * N * d * (2 * d) + 2 * N * 1568 * d
     head = 2 * P * d * 1568
-    return {"dino": dino, "betr_linear": betr_lin, "betr_attention": betr_att, "fusion_head": fusion + head,
-            "total": dino + betr_lin + betr_att + fusion + head}
+    total = dino + betr_lin + betr_att + fusion + head
+    # What this engine EXECUTES: the decoder's last block runs only for the query view's P tokens behind its K/V projection
+    # (attention from a query window, proj / fc1 / fc2 on the gathered rows; csrc/bd_engine.cu:run_block_query_rows) -- the
+    # reference computes the other (T-1)*P rows and drops them (betr.py:419-430).  Identical results, fewer FLOPs: every rate this
+    # file reports is computed from the executed FLOPs, `total` is kept as the reference algorithm's count.
+    last_lin_exec = 2 * N * d * (3 * d) + 2 * P * d * (9 * d)
+    last_att_exec = 4 * P * N * d
+    betr_lin_exec = betr_lin - (2 * N * d * (12 * d) - last_lin_exec) if T > 1 else betr_lin
+    betr_att_exec = betr_att - (4 * N * N * d - last_att_exec) if T > 1 else betr_att
+    return {"dino": dino, "betr_linear": betr_lin, "betr_attention": betr_att, "fusion_head": fusion + head, "total": total,
+            "betr_linear_executed": betr_lin_exec, "betr_attention_executed": betr_att_exec,
+            "executed": dino + betr_lin_exec + betr_att_exec + fusion + head}
 
 
 def ncu_traffic_bytes(kernel_substr):
@@ -472,26 +482,31 @@ def run_ours(args, rank, world, local_rank):
     # roofline of the dominant north-star kernel: the decoder (BETR) attention kernel, attn_tc2_kernel<96>.
     # Algorithmic FLOPs per launch = 4*N^2*d per sample (QK^T and PV only) x B samples; duration = in-step CUDA events.
     fl = flops_per_query()
-    att_flops_launch = B * fl["betr_attention"] / 12.0
+    att_flops_launch = B * fl["betr_attention"] / 12.0          # a full launch: all N = T*P query rows
+    att_flops_step = B * fl["betr_attention_executed"]           # 11 full launches + the last block's query-window launch (P rows)
     att_launches = max(kernel_n["attention"], 1)
     att_ms_launch = kernel_ms["attention"] / att_launches
     peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-    achieved = att_flops_launch / (att_ms_launch / 1e3) / 1e12 if att_ms_launch > 0 else 0.0
+    achieved = att_flops_step / (kernel_ms["attention"] / 1e3) / 1e12 if kernel_ms["attention"] > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "attn_tc2_kernel<96> (BETR joint attention, 8 heads x 96, N = T*P = 1536, B = 64)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "traffic": ncu_traffic_bytes("attn_tc2_kernel<96>"),
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}): kernel timed inside the step",
                 "flops_per_launch": att_flops_launch, "ms_per_launch": att_ms_launch, "launches_per_step": att_launches,
+                "flops_per_step": att_flops_step, "ms_per_step": kernel_ms["attention"],
+                "note": "achieved = executed FLOPs of all launches of the step / their summed in-step duration: 11 full launches "
+                        "(flops_per_launch each) + 1 query-window launch of the last block (1/T of the rows)",
                 "algorithmic_bytes_per_launch": 4 * B * 8 * 1536 * 96 * 2}
     dino_att_flops = B * T * 12 * 4 * 261 * 261 * 768
     roofline_dino_attention = {"achieved": dino_att_flops / (kernel_ms["attention_dino"] / 1e3) / 1e12 if kernel_ms["attention_dino"] > 0 else 0.0,
                                "peak": peak, "unit": "TFLOP/s", "ms_per_step": kernel_ms["attention_dino"]}
     gemm_ms = sum(kernel_ms[k] for k in ("gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_other"))
-    gemm_flops_step = B * (fl["total"] - fl["betr_attention"]) - dino_att_flops
+    gemm_flops_step = B * (fl["executed"] - fl["betr_attention_executed"]) - dino_att_flops
     roofline_gemm = {"bound": "tensor", "achieved": gemm_flops_step / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0, "peak": peak,
                      "unit": "TFLOP/s"}
     roofline_gemm["frac"] = roofline_gemm["achieved"] / peak if peak else None
-    roofline_e2e = {"achieved": fl["total"] * value / world / 1e12, "peak": peak, "unit": "TFLOP/s"}
+    roofline_e2e = {"achieved": fl["executed"] * value / world / 1e12, "peak": peak, "unit": "TFLOP/s",
+                    "flops_per_query_executed": fl["executed"], "flops_per_query_reference_algorithm": fl["total"]}
     roofline_e2e["frac"] = roofline_e2e["achieved"] / peak if peak else None
 
     # ---- e2e: C-ABI call with HOST buffers (pinned), H2D + D2H inside the timed region ----
@@ -647,7 +662,7 @@ def run_ours(args, rank, world, local_rank):
                     "sync_call_api": "bd_forward_host (one blocking call per batch)"},
             "e2e_device_rasterised_inputs": e2e_px,
             "gpu_launches": int(launches), "kernel_ms_per_step": kernel_ms, "kernel_launches_per_step": kernel_n,
-            "clocks": clocks, "flops_per_query": fl["total"],
+            "clocks": clocks, "flops_per_query": fl["total"], "flops_per_query_executed": fl["executed"],
         }
         if per_rank_ms is not None:
             line["per_rank_ms_per_step"] = {"min": min(per_rank_ms), "max": max(per_rank_ms), "rank0": per_rank_ms[0], "all": per_rank_ms,
@@ -727,10 +742,10 @@ def run_config4(args, rank, world, local_rank):
     kernel_ms = {name: ms_arr[i] for i, name in enumerate(_lib.PROF_CATS)}
     fl = flops_per_query(T=T, P=576, n_tok=581)
     N = T * 576
-    att_flops = mb * 4.0 * N * N * 768
+    att_flops = mb * 4.0 * N * N * 768                       # a full launch; the last block's query-window launch does 1/T of it
     att_ms = kernel_ms["attention"] / max(int(n_arr[_lib.PROF_CATS.index("attention")]), 1)
     peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-    ach = att_flops / (att_ms / 1e3) / 1e12 if att_ms > 0 else 0.0
+    ach = mb * fl["betr_attention_executed"] / (kernel_ms["attention"] / 1e3) / 1e12 if kernel_ms["attention"] > 0 else 0.0
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -741,8 +756,9 @@ def run_config4(args, rank, world, local_rank):
                        "l2": "activations of one micro-batch (>= 1 GB) exceed L2", "parallelism": f"query-shard x{world}"},
             "roofline": {"bound": "tensor", "kernel": f"attn_tc2_kernel<96> (N = {N}, {mb} queries x 8 heads per launch)", "achieved": ach, "peak": peak,
                          "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": None, "flops_per_launch": att_flops, "ms_per_launch": att_ms},
-            "roofline_e2e": {"achieved": fl["total"] * value / world / 1e12, "peak": peak, "unit": "TFLOP/s",
-                             "frac": fl["total"] * value / world / 1e12 / peak if peak else None},
+            "roofline_e2e": {"achieved": fl["executed"] * value / world / 1e12, "peak": peak, "unit": "TFLOP/s",
+                             "frac": fl["executed"] * value / world / 1e12 / peak if peak else None,
+                             "flops_per_query_executed": fl["executed"], "flops_per_query_reference_algorithm": fl["total"]},
             "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "kernel_ms_per_micro_batch": kernel_ms, "clocks": clocks,
             "flops_per_query": fl["total"]}), flush=True)
     return 0

@@ -92,6 +92,11 @@ struct Att2Cfg {
 struct Att2Args {
   int heads, seq, seq_pad, BH;
   int q_off;         // first query row handled by this kernel (rows [0, q_off) are done by attention_prefix_rows)
+  // Query window (the decoder's LAST layer: only the query view's tokens feed the head, betr.py:419-430): when win_idx != nullptr
+  // sequence l attends only from its rows [win_idx[l] * win_rows, +win_rows) -- over ALL keys -- and O is the compact
+  // [L, win_rows, heads*HD] tensor.  q_off must be 0 then.
+  const long long* win_idx;
+  int win_rows;
   float scale_log2;
   long long* trace;  // debug: per-role clock64 stamps of CTA 0's first items (nullptr in production)
 };
@@ -170,7 +175,9 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
   const int lane = threadIdx.x & 31;
   const int seq = args.seq, seq_pad = args.seq_pad;
   const int q_off = args.q_off;
-  const int n_qt = (seq - q_off + A2_BQ - 1) / A2_BQ;    // query tiles per sequence
+  const bool windowed = args.win_idx != nullptr;
+  const int q_end = windowed ? args.win_rows : seq;      // query rows (relative to the window start) end here
+  const int n_qt = (q_end - q_off + A2_BQ - 1) / A2_BQ;  // query tiles per sequence
   const int n_pairs = (n_qt + 1) / 2;
   const int n_items = args.BH * n_pairs;
   const int n_kv = (seq + BKV - 1) / BKV;
@@ -225,8 +232,9 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
     for (int item_f = blockIdx.x; item_f < n_items; item_f += gridDim.x, ++it) {
       const int item = item_f;
       const int bh = item / n_pairs, pair = item % n_pairs;
-      const int q0 = q_off + pair * 2 * A2_BQ;
-      const bool act1 = q0 + A2_BQ < seq;
+      const int qrel = q_off + pair * 2 * A2_BQ;
+      const bool act1 = qrel + A2_BQ < q_end;
+      const int q0 = qrel + (windowed ? static_cast<int>(args.win_idx[bh / args.heads]) * args.win_rows : 0);
       const int qb = it % QBUF;
       uint8_t* sQi = sQ + qb * 2 * Cfg::Q_TILE;
       if (lane == 0) A2_TRACE(3, it * 8 + 0);
@@ -273,7 +281,7 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
     for (int item_f = blockIdx.x; item_f < n_items; item_f += gridDim.x, ++it) {
       const int item = item_f;
       const int pair = item % n_pairs;
-      const bool act1 = q_off + pair * 2 * A2_BQ + A2_BQ < seq;
+      const bool act1 = q_off + pair * 2 * A2_BQ + A2_BQ < q_end;
       const int qb = it % QBUF;
       const uint32_t q_lo = q_lo0 + qb * ((2 * Cfg::Q_TILE) >> 4);
       const uint32_t q_lo1 = q_lo + (Cfg::Q_TILE >> 4);
@@ -363,8 +371,8 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
     for (int item_f = blockIdx.x; item_f < n_items; item_f += gridDim.x, ++it) {
       const int item = item_f;
       const int bh = item / n_pairs, pair = item % n_pairs;
-      const int q0 = q_off + pair * 2 * A2_BQ + g * A2_BQ;
-      if (q0 >= seq) {  // inactive second tile: the whole group skips this item (but still releases its last staging tile:
+      const int q0 = q_off + pair * 2 * A2_BQ + g * A2_BQ;   // relative to the window start (= absolute without a window): the O row
+      if (q0 >= q_end) {  // inactive second tile: the whole group skips this item (but still releases its last staging tile:
                         // the producer may need that Q buffer before this group becomes active again)
         if (storer && pend_qb >= 0) {
           bulk_wait_group_read<0>();
@@ -377,7 +385,7 @@ attn_tc2_kernel(const __grid_constant__ Att2Maps tm, const Att2Args args) {
       // Anti-phase: while one group runs its exp loop (MUFU-bound) the other one reads S from TMEM, takes the row
       // maximum, stores P and hands it to the MMA warp.  Strict alternation g0, g1, g0, ... per key tile; group 1 opens
       // group 0's first turn of every item.  Items whose second tile is inactive run group 0 alone, without turns.
-      const bool turns = (q_off + pair * 2 * A2_BQ + A2_BQ < seq) && (n_kv > A2_TURNS_MIN_KV);
+      const bool turns = (q_off + pair * 2 * A2_BQ + A2_BQ < q_end) && (n_kv > A2_TURNS_MIN_KV);
       float m_run = -INFINITY, l_run = 0.f;
       if (turns && g == 1) a2_turn_pass(1, l_run, turn_slot + 1024);
       for (int j = 0; j < n_kv; ++j) {
@@ -598,18 +606,19 @@ bool get_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d
 
 template <int HD>
 static cudaError_t launch_att2(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int seq, int seq_pad,
-                               float scale, int q_off, cudaStream_t s) {
+                               float scale, int q_off, cudaStream_t s, const long long* win_idx = nullptr, int win_rows = 0) {
   using Cfg = Att2Cfg<HD>;
   const int BH = L * heads;
   const uint64_t qk_rows = static_cast<uint64_t>(BH) * seq_pad, v_rows = static_cast<uint64_t>(BH) * HD;
   const uint64_t o_cols = static_cast<uint64_t>(heads) * HD;
+  const uint64_t o_rows = win_idx ? win_rows : seq;   // rows per sequence of the output tensor (compact with a query window)
   Att2Maps tm;
   bool ok = get_tmap_2d_bf16(&tm.q, Q, qk_rows, HD, HD, 64, A2_BQ) && get_tmap_2d_bf16(&tm.k, K, qk_rows, HD, HD, 64, Cfg::BKV) &&
             get_tmap_2d_bf16(&tm.v, Vt, v_rows, seq_pad, seq_pad, 64, HD) &&
-            get_tmap_3d_bf16(&tm.o, O, o_cols, seq, L, o_cols * 2, static_cast<uint64_t>(seq) * o_cols * 2, 64, A2_BQ);
+            get_tmap_3d_bf16(&tm.o, O, o_cols, o_rows, L, o_cols * 2, static_cast<uint64_t>(o_rows) * o_cols * 2, 64, A2_BQ);
   if (ok && Cfg::SPLIT) {
     ok = get_tmap_2d_bf16(&tm.q2, Q, qk_rows, HD, HD, 32, A2_BQ) && get_tmap_2d_bf16(&tm.k2, K, qk_rows, HD, HD, 32, Cfg::BKV) &&
-         get_tmap_3d_bf16(&tm.o2, O, o_cols, seq, L, o_cols * 2, static_cast<uint64_t>(seq) * o_cols * 2, 32, A2_BQ);
+         get_tmap_3d_bf16(&tm.o2, O, o_cols, o_rows, L, o_cols * 2, static_cast<uint64_t>(o_rows) * o_cols * 2, 32, A2_BQ);
   } else if (ok) {
     tm.q2 = tm.q; tm.k2 = tm.k; tm.o2 = tm.o;
   }
@@ -620,10 +629,10 @@ static cudaError_t launch_att2(const bf16* Q, const bf16* K, const bf16* Vt, bf1
   cudaError_t aerr = tc_ensure_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES);
   if (aerr != cudaSuccess) return aerr;
   const int n_sms = tc_num_sms();
-  const int n_qt = (seq - q_off + A2_BQ - 1) / A2_BQ;
+  const int n_qt = ((win_idx ? win_rows : seq) - q_off + A2_BQ - 1) / A2_BQ;
   const int n_items = BH * ((n_qt + 1) / 2);
   const int grid = n_items < n_sms ? n_items : n_sms;
-  Att2Args a{heads, seq, seq_pad, BH, q_off, scale * 1.4426950408889634f, g_att2_trace};
+  Att2Args a{heads, seq, seq_pad, BH, q_off, win_idx, win_rows, scale * 1.4426950408889634f, g_att2_trace};
   kern<<<grid, A2_THREADS, Cfg::SMEM_BYTES, s>>>(tm, a);
   return cudaGetLastError();
 }
@@ -780,6 +789,16 @@ cudaError_t attention_tc(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, 
     if (q_off && (err = launch_prefix<64>(Q, K, Vt, O, L, heads, seq, seq_pad, q_off, scale, s)) != cudaSuccess) return err;
     return launch_att2<64>(Q, K, Vt, O, L, heads, seq, seq_pad, scale, q_off, s);
   }
+  return cudaErrorInvalidValue;
+}
+
+// Attention from a window of query rows per sequence (rows [win_idx[l] * win_rows, +win_rows) over all `seq` keys) into the compact
+// O [L, win_rows, heads*head_dim]: the decoder's last layer, whose other rows nothing reads.
+cudaError_t attention_tc_window(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int head_dim, int seq,
+                                int seq_pad, float scale, const long long* win_idx, int win_rows, cudaStream_t s) {
+  if (seq_pad % 128 != 0 || seq > seq_pad || seq <= 0 || !win_idx || win_rows <= 0 || win_rows > seq) return cudaErrorInvalidValue;
+  if (head_dim == 96) return launch_att2<96>(Q, K, Vt, O, L, heads, seq, seq_pad, scale, 0, s, win_idx, win_rows);
+  if (head_dim == 64) return launch_att2<64>(Q, K, Vt, O, L, heads, seq, seq_pad, scale, 0, s, win_idx, win_rows);
   return cudaErrorInvalidValue;
 }
 

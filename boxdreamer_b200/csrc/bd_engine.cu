@@ -429,6 +429,40 @@ static int run_block(bd_engine* e, float* X, const std::string& p, int L, int se
   return BD_OK;
 }
 
+// The decoder's LAST block on the tensor path.  Only the query view's P tokens of each sequence reach the head (betr.py:419-430
+// gathers them), so everything behind this block's K/V projection is computed for those rows only: attention from the query
+// window over all T*P keys into a compact O, then proj / LayerNorm / MLP on the B*P gathered residual rows `Xc` (fp32, compact).
+// Per-row arithmetic is unchanged (same k order in every GEMM, same key-tile order in the attention), so the head sees the
+// bit-identical tokens; the block does 1/T of its attention and 1/T of 3 of its 4 GEMMs.  BD_LAST_LAYER_PRUNE=0 disables it.
+static int run_block_query_rows(bd_engine* e, float* X, const std::string& p, int B, int T, int P, int seq_pad, int heads, int hd,
+                                float ln_eps, const int64_t* query_idx, float* Xc, cudaStream_t s) {
+  const int seq = T * P, M = B * seq, Mq = B * P, d = e->d;
+  LAUNCH(BD_PROF_LAYERNORM, 1, ln_act(e, X, WF(e, p + "norm1.weight"), WF(e, p + "norm1.bias"), ln_eps, M, s));
+  GemmEpi q;
+  q.bias = WF(e, p + "attn.qkv.bias");
+  q.q = e->Q; q.k = e->K; q.v = e->V;
+  q.q_norm_w = WF(e, p + "attn.q_norm.weight");
+  q.k_norm_w = WF(e, p + "attn.k_norm.weight");
+  q.seq = seq; q.seq_pad = seq_pad; q.heads = heads; q.head_dim = hd; q.rms_eps = 1e-6f;
+  LAUNCH(BD_PROF_GEMM_QKV, 1, linear(e, e->H, p + "attn.qkv.weight", M, 3 * d, d, EPI_QKV, q, s));
+  LAUNCH(BD_PROF_ATTENTION, 1,
+         attention_tc_window(reinterpret_cast<const bf16*>(e->Q), reinterpret_cast<const bf16*>(e->K), reinterpret_cast<const bf16*>(e->V),
+                             reinterpret_cast<bf16*>(e->O), B, heads, hd, seq, seq_pad, 1.0f / sqrtf(static_cast<float>(hd)),
+                             reinterpret_cast<const long long*>(query_idx), P, s));
+  LAUNCH(BD_PROF_GLUE, 1, gather_query(X, query_idx, Xc, nullptr, B, T, P, d, s));
+  GemmEpi pr;
+  pr.bias = WF(e, p + "attn.proj.bias"); pr.out_f32 = Xc; pr.ldo = d;
+  LAUNCH(BD_PROF_GEMM_PROJ, 1, linear(e, e->O, p + "attn.proj.weight", Mq, d, d, EPI_RESID, pr, s));
+  LAUNCH(BD_PROF_LAYERNORM, 1, ln_act(e, Xc, WF(e, p + "norm2.weight"), WF(e, p + "norm2.bias"), ln_eps, Mq, s));
+  GemmEpi f1;
+  f1.bias = WF(e, p + "mlp.fc1.bias"); f1.out_act = e->G;
+  LAUNCH(BD_PROF_GEMM_FC1, 1, linear(e, e->H, p + "mlp.fc1.weight", Mq, 4 * d, d, EPI_GELU, f1, s));
+  GemmEpi f2;
+  f2.bias = WF(e, p + "mlp.fc2.bias"); f2.out_f32 = Xc; f2.ldo = d;
+  LAUNCH(BD_PROF_GEMM_FC2, 1, linear(e, e->G, p + "mlp.fc2.weight", Mq, d, 4 * d, EPI_RESID, f2, s));
+  return BD_OK;
+}
+
 // all `layers` blocks "<prefix><i>." over L sequences of `seq` tokens
 static int run_layers(bd_engine* e, float* X, const std::string& prefix, int layers, int L, int seq, int seq_pad, int heads, int hd,
                       float ln_eps, bool qk_norm, const char* g1, const char* g2, int attn_cat, cudaStream_t s) {
@@ -495,12 +529,22 @@ static int decoder_forward_impl(bd_engine* e, const void* bbox_feat, int dtype, 
   LAUNCH(BD_PROF_GLUE, 1, betr_fuse(e->PF, e->R, WF(e, "decoder.bbox_learnable_query"), e->pos_dec, query_idx, e->X_dec, B, T, P, d, 1e-6f, s));
   const int seq = T * P, seq_pad = (seq + 127) / 128 * 128;
   {
-    int r = run_layers(e, e->X_dec, "decoder.attn.", e->cfg.dec_layers, B, seq, seq_pad, e->cfg.dec_heads, e->hd_dec, 1e-5f, true, nullptr,
+    const char* pe = getenv("BD_LAST_LAYER_PRUNE");   // read per call so that a test can flip it
+    const bool prune = e->tc && T > 1 && e->cfg.dec_layers >= 1 && !(pe && atoi(pe) == 0);
+    const int full_layers = prune ? e->cfg.dec_layers - 1 : e->cfg.dec_layers;
+    int r = run_layers(e, e->X_dec, "decoder.attn.", full_layers, B, seq, seq_pad, e->cfg.dec_heads, e->hd_dec, 1e-5f, true, nullptr,
                        nullptr, BD_PROF_ATTENTION, s);
     if (r != BD_OK) return r;
+    if (prune) {   // last block on the query view's rows only; `R` (the adapter branch, consumed by betr_fuse) is free by now
+      r = run_block_query_rows(e, e->X_dec, "decoder.attn." + std::to_string(full_layers) + ".", B, T, P, seq_pad, e->cfg.dec_heads, e->hd_dec,
+                               1e-5f, query_idx, e->R, s);
+      if (r != BD_OK) return r;
+      LAUNCH(BD_PROF_GLUE, 1, cast_f32_to_bf16(e->R, reinterpret_cast<bf16*>(e->Xq), static_cast<size_t>(B) * P * d, s));
+    } else {
+      LAUNCH(BD_PROF_GLUE, 1, gather_query(e->X_dec, query_idx, e->tc ? nullptr : reinterpret_cast<float*>(e->Xq),
+                                           e->tc ? reinterpret_cast<bf16*>(e->Xq) : nullptr, B, T, P, d, s));
+    }
   }
-  LAUNCH(BD_PROF_GLUE, 1, gather_query(e->X_dec, query_idx, e->tc ? nullptr : reinterpret_cast<float*>(e->Xq),
-                                       e->tc ? reinterpret_cast<bf16*>(e->Xq) : nullptr, B, T, P, d, s));
   float* lg = logits_out ? logits_out : e->logits;
   GemmEpi bp;
   bp.bias = WF(e, "decoder.bbox_proj.bias"); bp.out_f32 = lg; bp.ldo = pp8;

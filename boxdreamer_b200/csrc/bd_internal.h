@@ -54,6 +54,8 @@ const char* tc_last_error();
 
 // --- SIMT fp32 path + memory-bound kernels (kernels_simt.cu) ---
 cudaError_t gemm_f32(const float* A, const float* W, int M, int N, int K, int epi, const GemmEpi& e, cudaStream_t s);
+cudaError_t attention_tc_window(const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int L, int heads, int head_dim, int seq,
+                                int seq_pad, float scale, const long long* win_idx, int win_rows, cudaStream_t s);
 cudaError_t attention_f32(const float* Q, const float* K, const float* V, float* O, int L, int heads, int head_dim,
                           int seq, int seq_pad, float scale, cudaStream_t s);
 // LayerNorm over the last dim (d), fp32 in; writes any of: fp32 out, bf16 out.  Row remap for the DINO tail:

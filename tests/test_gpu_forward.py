@@ -345,3 +345,24 @@ def test_pipelined_host_entry_matches_blocking_call(weights):
                     assert all(torch.equal(g, r) for g, r in zip(got[i - 1], ref[i - 1])), f"batch {i - 1} (px={use_px})"
             eng.forward_host_wait((len(batches) - 1) & 1)
             assert all(torch.equal(g, r) for g, r in zip(got[-1], ref[-1]))
+
+
+@pytest.mark.parametrize("B,T,qidx", [(3, 3, [2, 0, 1]), (2, 6, [5, 3])])
+def test_last_decoder_block_on_query_rows_is_bit_identical(weights, monkeypatch, B, T, qidx):
+    """The tensor path runs the decoder's last block only for the query view's tokens (attention from a query window over all
+    keys, proj / LayerNorm / MLP on the gathered rows) -- the other rows are never read (betr.py:419-430).  Per-row arithmetic
+    is unchanged, so the logits must not change by a single bit against BD_LAST_LAYER_PRUNE=0."""
+    data = synth.synth_inputs(B, T, 224, seed=311)
+    data["query_idx"] = torch.tensor(qidx, dtype=torch.int64)
+    d = _to_cuda({k: (v.to(torch.bfloat16) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in data.items()})
+    m = _model(weights, "bf16")
+    eng = m._engine_for(d["images"], B, T)
+    feats = eng.dino_forward(d["images"].view(B * T, 3, 224, 224).contiguous())
+    outs = []
+    for flag in ("1", "0", "1"):
+        monkeypatch.setenv("BD_LAST_LAYER_PRUNE", flag)
+        heat, logits = eng.decoder_forward(d["bbox_feat"].contiguous(), feats, d["query_idx"], want_logits=True)
+        torch.cuda.synchronize()
+        outs.append((heat.clone(), logits.clone()))
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0]), "pruned last block changed the logits"
+    assert torch.equal(outs[0][1], outs[2][1])

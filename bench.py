@@ -515,7 +515,7 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(2):
             eng.forward_host(h_images, h_bbox, h_qidx, h_X, h_K)
         barrier()
-        e2e_steps = max(2, min(args.steps, 10))
+        e2e_steps = max(2, min(args.steps, 20))
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             eng.forward_host(h_images, h_bbox, h_qidx, h_X, h_K)  # synchronises on return

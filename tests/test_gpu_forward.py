@@ -366,3 +366,26 @@ def test_last_decoder_block_on_query_rows_is_bit_identical(weights, monkeypatch,
         outs.append((heat.clone(), logits.clone()))
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0]), "pruned last block changed the logits"
     assert torch.equal(outs[0][1], outs[2][1])
+
+
+def test_last_decoder_block_on_query_rows_336px(monkeypatch):
+    """Same bit-identity at 336 px: P = 576 tokens per view is not a multiple of the 128-row query tile, so the query window ends
+    inside a tile (rows beyond it belong to the next view or to the padding and are clipped by the compact O tensor map)."""
+    dec, dino = synth.synth_decoder_state_dict(0), synth.synth_dino_state_dict(0)
+    m = BoxDreamer(_config(336), precision="bf16")
+    m.load_state_dict(dec, strict=True)
+    m.rgb_encoder.model.load_state_dict(dino, strict=True)
+    m = m.cuda().eval()
+    B, T = 2, 3
+    data = synth.synth_inputs(B, T, 336, seed=312)
+    data["query_idx"] = torch.tensor([2, 0], dtype=torch.int64)   # last view: the window ends at the sequence end
+    d = _to_cuda({k: (v.to(torch.bfloat16) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in data.items()})
+    eng = m._engine_for(d["images"], B, T)
+    feats = eng.dino_forward(d["images"].view(B * T, 3, 336, 336).contiguous())
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("BD_LAST_LAYER_PRUNE", flag)
+        heat, logits = eng.decoder_forward(d["bbox_feat"].contiguous(), feats, d["query_idx"], want_logits=True)
+        torch.cuda.synchronize()
+        outs.append(logits.clone())
+    assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])

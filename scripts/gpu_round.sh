@@ -7,7 +7,7 @@ echo "=== bench"; timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out
 echo "=== bench reference"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "exit $?"; cat gpurun_out/bench_ref.json
 echo "=== kernels"; timeout 600 python scripts/bench_kernels.py > gpurun_out/bench_kernels.json 2>&1; echo "exit $?"
 if [ "$NO_NCU" != "1" ]; then
-echo "=== ncu launch list (218 launches per step; ~600 set-up launches + 3 warm-up steps skipped)"
+echo "=== ncu launch list (219 launches per step; ~600 set-up launches + 3 warm-up steps skipped)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1260 -c 440 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --quick > gpurun_out/ncu_launch.log 2>&1; echo "exit $?"
 echo "=== ncu full: decoder attention"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_tc2_kernel -s 60 -c 2 -o gpurun_out/prof_attn -f python bench.py --steps 1 --warmup 3 --quick > gpurun_out/ncu_attn.log 2>&1; echo "exit $?"

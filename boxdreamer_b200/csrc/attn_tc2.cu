@@ -687,17 +687,24 @@ __global__ void __launch_bounds__(PFX_WARPS * 32) attention_prefix_rows_kernel(c
   const int n_chunks = (seq + NT * 8 - 1) / (NT * 8);
   for (int ch = 0; ch < n_chunks; ++ch) {
     const int key0 = ch * NT * 8;
-    // ---- scores: NT tiles of 8 keys ----
+    // ---- scores: NT tiles of 8 keys.  All K loads of the chunk are issued before the first MMA (the kernel is bound by the
+    // round trips to L2 / HBM, not by bandwidth: with the loads interleaved into the MMA chain only a few KB per warp were in flight)
     float sc[NT][4];
+    uint4 kfrag[NT][KS / 2];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-      sc[t][0] = sc[t][1] = sc[t][2] = sc[t][3] = 0.f;
       int key = key0 + 16 * (t >> 1) + 4 * (g >> 1) + (g & 1) + 2 * (t & 1);   // the key this lane's B fragment column (n = g) holds
       key = key < seq_pad ? key : seq_pad - 1;
       const bf16* kr = Kb + static_cast<long long>(key) * HD + q * DPL;
 #pragma unroll
+      for (int s2 = 0; s2 < KS; s2 += 2) kfrag[t][s2 >> 1] = __ldg(reinterpret_cast<const uint4*>(kr + 4 * s2));   // dims of k-steps s2, s2+1
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      sc[t][0] = sc[t][1] = sc[t][2] = sc[t][3] = 0.f;
+#pragma unroll
       for (int s2 = 0; s2 < KS; s2 += 2) {
-        const uint4 kv = __ldg(reinterpret_cast<const uint4*>(kr + 4 * s2));   // dims of k-steps s2, s2+1
+        const uint4 kv = kfrag[t][s2 >> 1];
         mma_bf16_16816(sc[t], qa0[s2], 0u, qa2[s2], 0u, kv.x, kv.y);
         mma_bf16_16816(sc[t], qa0[s2 + 1], 0u, qa2[s2 + 1], 0u, kv.z, kv.w);
       }
@@ -731,15 +738,23 @@ __global__ void __launch_bounds__(PFX_WARPS * 32) attention_prefix_rows_kernel(c
     l_run = l_run * alpha + psum;
 #pragma unroll
     for (int t = 0; t < OT; ++t) { o[t][0] *= alpha; o[t][1] *= alpha; }
-    // ---- O += P V : k-step T = tiles 2T, 2T+1 = keys key0 + 16T + 4q .. +3 (one 8-byte load of V^T per output tile) ----
+    // ---- O += P V : k-step T = tiles 2T, 2T+1 = keys key0 + 16T + 4q .. +3 (one 8-byte load of V^T per output tile); the loads of
+    // half a chunk are issued together, ahead of their MMAs
 #pragma unroll
-    for (int T2 = 0; T2 < NT / 2; ++T2) {
-      int kk = key0 + 16 * T2 + 4 * q;
-      kk = kk + 4 <= seq_pad ? kk : seq_pad - 4;    // (P is zero there)
+    for (int h = 0; h < 2; ++h) {
+      uint2 vfrag[NT / 4][OT];
 #pragma unroll
-      for (int t = 0; t < OT; ++t) {
-        const uint2 vv = __ldg(reinterpret_cast<const uint2*>(Vb + static_cast<long long>(8 * t + g) * seq_pad + kk));
-        mma_bf16_16816(o[t], pa[2 * T2], 0u, pa[2 * T2 + 1], 0u, vv.x, vv.y);
+      for (int T2 = 0; T2 < NT / 4; ++T2) {
+        int kk = key0 + 16 * (h * (NT / 4) + T2) + 4 * q;
+        kk = kk + 4 <= seq_pad ? kk : seq_pad - 4;    // (P is zero there)
+#pragma unroll
+        for (int t = 0; t < OT; ++t) vfrag[T2][t] = __ldg(reinterpret_cast<const uint2*>(Vb + static_cast<long long>(8 * t + g) * seq_pad + kk));
+      }
+#pragma unroll
+      for (int T2 = 0; T2 < NT / 4; ++T2) {
+        const int TT = h * (NT / 4) + T2;
+#pragma unroll
+        for (int t = 0; t < OT; ++t) mma_bf16_16816(o[t], pa[2 * TT], 0u, pa[2 * TT + 1], 0u, vfrag[T2][t].x, vfrag[T2][t].y);
       }
     }
   }

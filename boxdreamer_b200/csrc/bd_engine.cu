@@ -655,7 +655,7 @@ extern "C" int bd_pnp(bd_handle e, const float* corners_px, const float* bbox3d,
   if (!corners_px || !bbox3d || !K || !poses_out) return fail(BD_ERR_INVALID, "bd_pnp: null argument");
   cudaError_t ce = pnp_solve(corners_px, bbox3d, K, poses_out, to_opts(opts), B, n_pts, reinterpret_cast<cudaStream_t>(stream));
   if (ce == cudaErrorNotSupported) return fail(BD_ERR_UNSUPPORTED, "bd_pnp: mode not built");
-  if (ce == cudaErrorInvalidValue) return fail(BD_ERR_INVALID, "bd_pnp: n_pts must be in [6,64]");
+  if (ce == cudaErrorInvalidValue) return fail(BD_ERR_INVALID, "bd_pnp: n_pts must be in [6,64] (iterative mode) / [6,256] (robust mode)");
   CK(ce);
   return BD_OK;
 }

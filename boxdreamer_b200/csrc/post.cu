@@ -158,10 +158,30 @@ cudaError_t corners_topk(const float* heat, float* corners_px, float* corners_no
 // A^T A by cyclic Jacobi) -> nearest rotation (Newton polar iteration) -> Levenberg-Marquardt on the pixel
 // reprojection error over all points, run to convergence, all in fp64.  One thread per query.
 
-static constexpr int PNP_MAXPTS = 64;   // pooled proposals of the dense multi-round path: 8 sub-batches x 8 corners
-typedef unsigned long long pmask_t;      // bit i = use point i
-static constexpr pmask_t PNP_ALL = ~0ull;
 #define BD_HD __host__ __device__
+static constexpr int PNP_MAXPTS = 64;        // iterative mode (thread-per-query kernel: the problem lives in local memory)
+static constexpr int PNP_MAXPTS_POOLED = 256;  // robust mode: pooled proposals of the dense multi-round path, 32 sub-batches x 8 corners
+                                               // (the reference hands all N*8 pairs to solvePnPRansac, box_utils.py:202-304)
+// point mask: bit i = use point i
+struct pmask_t {
+  unsigned long long w[PNP_MAXPTS_POOLED / 64];
+};
+BD_HD inline pmask_t pm_none() { pmask_t m; for (int k = 0; k < PNP_MAXPTS_POOLED / 64; ++k) m.w[k] = 0ull; return m; }
+BD_HD inline pmask_t pm_first(int n) {   // points 0 .. n-1
+  pmask_t m;
+  for (int k = 0; k < PNP_MAXPTS_POOLED / 64; ++k) {
+    const int r = n - 64 * k;
+    m.w[k] = r >= 64 ? ~0ull : (r <= 0 ? 0ull : ((1ull << r) - 1ull));
+  }
+  return m;
+}
+BD_HD inline bool pm_test(const pmask_t& m, int i) { return (m.w[i >> 6] >> (i & 63)) & 1ull; }
+BD_HD inline void pm_set(pmask_t& m, int i) { m.w[i >> 6] |= 1ull << (i & 63); }
+BD_HD inline bool pm_equal(const pmask_t& a, const pmask_t& b) {
+  bool eq = true;
+  for (int k = 0; k < PNP_MAXPTS_POOLED / 64; ++k) eq = eq && a.w[k] == b.w[k];
+  return eq;
+}
 
 // Cyclic Jacobi on a symmetric 12x12 (row-major, flat).  NOTE: written with flat indexing and non-unrolled inner
 // loops on purpose -- nvcc 12.9 miscompiles the fully unrolled two-pass update on a `double (&)[12][12]` for sm_100a
@@ -420,35 +440,44 @@ BD_HD bool solve6(const double (&H)[6][6], const double (&g)[6], double lam, dou
   return true;
 }
 
-struct PnpProblem {
-  double X[PNP_MAXPTS][3];
-  double uv[PNP_MAXPTS][2];
+template <int NP>
+struct PnpProblemT {
+  double X[NP][3];
+  double uv[NP][2];
   double fx, fy, cx, cy;
   int n;
 };
-// The LM / cost routines take a point mask (bit i = use point i) so hypothesis refits can share one problem.
+typedef PnpProblemT<PNP_MAXPTS> PnpProblem;
+typedef PnpProblemT<PNP_MAXPTS_POOLED> PnpProblemPooled;
+// The LM / cost routines take an optional point mask (nullptr = all points) so hypothesis refits can share one problem.
 
-BD_HD double reproj_cost(const PnpProblem& pb, const double (&R)[3][3], const double (&t)[3], double (*res)[2],
-                              double (*Xc)[3], pmask_t mask = PNP_ALL) {
+// camera-frame point and pixel residual of point i
+template <int NP>
+BD_HD inline void pnp_point(const PnpProblemT<NP>& pb, int i, const double (&R)[3][3], const double (&t)[3], double (&xc)[3], double& ru,
+                            double& rv) {
+  for (int a = 0; a < 3; ++a) xc[a] = R[a][0] * pb.X[i][0] + R[a][1] * pb.X[i][1] + R[a][2] * pb.X[i][2] + t[a];
+  ru = pb.fx * xc[0] / xc[2] + pb.cx - pb.uv[i][0];
+  rv = pb.fy * xc[1] / xc[2] + pb.cy - pb.uv[i][1];
+}
+
+template <int NP>
+BD_HD double reproj_cost(const PnpProblemT<NP>& pb, const double (&R)[3][3], const double (&t)[3], const pmask_t* mask = nullptr) {
   double cost = 0.0;
   for (int i = 0; i < pb.n; ++i) {
-    if (!((mask >> i) & 1ull)) { if (res) { res[i][0] = 0.0; res[i][1] = 0.0; } continue; }
-    double xc[3];
-    for (int a = 0; a < 3; ++a) xc[a] = R[a][0] * pb.X[i][0] + R[a][1] * pb.X[i][1] + R[a][2] * pb.X[i][2] + t[a];
-    const double ru = pb.fx * xc[0] / xc[2] + pb.cx - pb.uv[i][0];
-    const double rv = pb.fy * xc[1] / xc[2] + pb.cy - pb.uv[i][1];
-    if (res) { res[i][0] = ru; res[i][1] = rv; }
-    if (Xc) { Xc[i][0] = xc[0]; Xc[i][1] = xc[1]; Xc[i][2] = xc[2]; }
+    if (mask && !pm_test(*mask, i)) continue;
+    double xc[3], ru, rv;
+    pnp_point(pb, i, R, t, xc, ru, rv);
     cost += ru * ru + rv * rv;
   }
   return cost;
 }
 
-BD_HD void pnp_dlt_init(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], pmask_t mask = PNP_ALL) {
+template <int NP>
+BD_HD void pnp_dlt_init(const PnpProblemT<NP>& pb, double (&R)[3][3], double (&t)[3], const pmask_t* mask = nullptr) {
   double A[144], V[144];
   for (int i = 0; i < 144; ++i) A[i] = 0.0;
   for (int i = 0; i < pb.n; ++i) {
-    if (!((mask >> i) & 1ull)) continue;
+    if (mask && !pm_test(*mask, i)) continue;
     const double xn = (pb.uv[i][0] - pb.cx) / pb.fx, yn = (pb.uv[i][1] - pb.cy) / pb.fy;
     double r1[12], r2[12];
     for (int j = 0; j < 12; ++j) { r1[j] = 0.0; r2[j] = 0.0; }
@@ -497,16 +526,21 @@ BD_HD void pnp_dlt_init(const PnpProblem& pb, double (&R)[3][3], double (&t)[3],
   nearest_rotation(R, 60);
 }
 
-BD_HD void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int max_iter, pmask_t mask = PNP_ALL) {
-  double res[PNP_MAXPTS][2], Xc[PNP_MAXPTS][3];
+// Levenberg-Marquardt on the pixel reprojection error.  The per-point camera-frame coordinates and residuals are recomputed
+// where they are needed (pnp_point: the same expressions, hence the same values) instead of being kept in per-thread arrays of
+// the maximum point count -- which is what capped the pooled path at 64 pairs.
+template <int NP>
+BD_HD void pnp_lm(const PnpProblemT<NP>& pb, double (&R)[3][3], double (&t)[3], int max_iter, const pmask_t* mask = nullptr) {
   double lam = 1e-3;
-  double cost = reproj_cost(pb, R, t, res, Xc, mask);
+  double cost = reproj_cost(pb, R, t, mask);
   for (int it = 0; it < max_iter; ++it) {
     double H[6][6], g[6];
     for (int a = 0; a < 6; ++a) { g[a] = 0.0; for (int b = 0; b < 6; ++b) H[a][b] = 0.0; }
     for (int i = 0; i < pb.n; ++i) {
-      if (!((mask >> i) & 1ull)) continue;
-      const double x = Xc[i][0], y = Xc[i][1], z = Xc[i][2];
+      if (mask && !pm_test(*mask, i)) continue;
+      double xc[3], ru, rv;
+      pnp_point(pb, i, R, t, xc, ru, rv);
+      const double x = xc[0], y = xc[1], z = xc[2];
       const double du[3] = {pb.fx / z, 0.0, -pb.fx * x / (z * z)};
       const double dv[3] = {0.0, pb.fy / z, -pb.fy * y / (z * z)};
       const double Y[3] = {x - t[0], y - t[1], z - t[2]};
@@ -521,7 +555,7 @@ BD_HD void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int m
       }
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
-        g[a] += ju[a] * res[i][0] + jv[a] * res[i][1];
+        g[a] += ju[a] * ru + jv[a] * rv;
 #pragma unroll
         for (int b = a; b < 6; ++b) H[a][b] += ju[a] * ju[b] + jv[a] * jv[b];
       }
@@ -542,8 +576,7 @@ BD_HD void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int m
         for (int b = 0; b < 3; ++b) Rn[a][b] = E[a][0] * R[0][b] + E[a][1] * R[1][b] + E[a][2] * R[2][b];
         tn[a] = t[a] + delta[3 + a];
       }
-      double resn[PNP_MAXPTS][2], Xcn[PNP_MAXPTS][3];
-      const double cn = reproj_cost(pb, Rn, tn, resn, Xcn, mask);
+      const double cn = reproj_cost(pb, Rn, tn, mask);
       if (isfinite(cn) && cn <= cost) {
         improved = true;
         step = 0.0;
@@ -552,10 +585,6 @@ BD_HD void pnp_lm(const PnpProblem& pb, double (&R)[3][3], double (&t)[3], int m
         dc = cost - cn;
         cost = cn;
         for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) R[a][b] = Rn[a][b]; t[a] = tn[a]; }
-        for (int i = 0; i < pb.n; ++i) {
-          res[i][0] = resn[i][0]; res[i][1] = resn[i][1];
-          Xc[i][0] = Xcn[i][0]; Xc[i][1] = Xcn[i][1]; Xc[i][2] = Xcn[i][2];
-        }
         lam = fmax(lam * 0.1, 1e-12);
         break;
       }
@@ -917,7 +946,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32) pnp_iterative_warp_kernel(const
 // is polished by LM on its inlier set.  Everything stays on the device; nothing is discarded.
 
 __device__ pmask_t nth_subset_mask(int n, int k, int idx) {  // idx-th k-subset of n points in lexicographic order
-  pmask_t mask = 0;
+  pmask_t mask = pm_none();
   int x = 0;
   for (int i = 0; i < k; ++i) {
     for (;; ++x) {
@@ -928,7 +957,7 @@ __device__ pmask_t nth_subset_mask(int n, int k, int idx) {  // idx-th k-subset 
       if (idx < c) break;
       idx -= static_cast<int>(c);
     }
-    mask |= 1ull << x;
+    pm_set(mask, x);
     ++x;
   }
   return mask;
@@ -948,12 +977,12 @@ __device__ __forceinline__ unsigned pnp_hash(unsigned seed, unsigned q, unsigned
 __global__ void __launch_bounds__(128) pnp_hypothesis_kernel(const float* __restrict__ corners, const float* __restrict__ bbox3d,
                                                              const float* __restrict__ Kmat, float* __restrict__ poses, int B,
                                                              int n_pts, int n_hyp, float thr_px, unsigned seed, int max_iter) {
-  __shared__ PnpProblem s_pb[4];
+  __shared__ PnpProblemPooled s_pb[4];   // 4 x 10.3 KB: the pooled path's points stay in shared memory
   __shared__ double s_seed[4][12];
   const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * 4 + wq;
   if (q >= B) return;
-  PnpProblem& pb = s_pb[wq];
+  PnpProblemPooled& pb = s_pb[wq];
   for (int i = lane; i < n_pts; i += 32) {
     for (int a = 0; a < 3; ++a) pb.X[i][a] = static_cast<double>(bbox3d[(static_cast<long long>(q) * n_pts + i) * 3 + a]);
     for (int a = 0; a < 2; ++a) pb.uv[i][a] = static_cast<double>(corners[(static_cast<long long>(q) * n_pts + i) * 2 + a]);
@@ -971,12 +1000,15 @@ __global__ void __launch_bounds__(128) pnp_hypothesis_kernel(const float* __rest
     for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) s_seed[wq][a * 3 + b] = R[a][b]; s_seed[wq][9 + a] = t[a]; }
   }
   __syncwarp();
-  const pmask_t all_mask = (n_pts >= 64) ? PNP_ALL : ((1ull << n_pts) - 1ull);
+  const pmask_t all_mask = pm_first(n_pts);
   const double thr2 = static_cast<double>(thr_px) * thr_px;
-  const int c6 = n_pts >= 6 ? n_choose_k(n_pts, 6) : 0, c5 = n_pts >= 5 ? n_choose_k(n_pts, 5) : 0, c4 = n_choose_k(n_pts, 4);
   // Few points (the 8 corners of one proposal): the subsets are enumerated.  Pooled proposals (n_pts > 12, dense
-  // multi-round path): the subset space is sampled -- seeded random 6-point subsets, each solved from scratch.
-  const bool enumerate = static_cast<long long>(c6) + c5 + c4 <= 4096;
+  // multi-round path): the subset space is sampled -- seeded random 6-point subsets, each solved from scratch: by lexicographic
+  // rank up to 64 points (C(64, 6) fits the 32-bit hash), by six seeded draws without replacement beyond.
+  const bool ranked = n_pts <= 64;
+  const int c6 = ranked && n_pts >= 6 ? n_choose_k(n_pts, 6) : 0, c5 = ranked && n_pts >= 5 ? n_choose_k(n_pts, 5) : 0,
+            c4 = ranked ? n_choose_k(n_pts, 4) : 0;
+  const bool enumerate = ranked && static_cast<long long>(c6) + c5 + c4 <= 4096;
   // best-so-far of this lane; hypothesis "-1" is the all-point seed itself
   double bestR[3][3], bestT[3];
   int best_inl = -1;
@@ -994,23 +1026,29 @@ __global__ void __launch_bounds__(128) pnp_hypothesis_kernel(const float* __rest
         else if (h < c6 + c5 + c4) m = nth_subset_mask(n_pts, 4, h - c6 - c5);
         else m = nth_subset_mask(n_pts, 5, static_cast<int>(pnp_hash(seed, q, h) % static_cast<unsigned>(c5 > 0 ? c5 : 1)));
         from_scratch = h < c6;   // 6-point subsets are solved from scratch (independent of the seed's basin)
-      } else {
+      } else if (ranked) {
         m = nth_subset_mask(n_pts, 6, static_cast<int>(pnp_hash(seed, q, h) % static_cast<unsigned>(c6)));
         from_scratch = true;
+      } else {
+        m = pm_none();
+        int picked = 0;
+        for (unsigned draw = 0; picked < 6; ++draw) {   // rejection on repeats: at most a handful of extra draws for n_pts > 64
+          const int i = static_cast<int>(pnp_hash(seed + 0x51ed2701u * (draw + 1u), q, h) % static_cast<unsigned>(n_pts));
+          if (!pm_test(m, i)) { pm_set(m, i); ++picked; }
+        }
+        from_scratch = true;
       }
-      if (from_scratch) pnp_dlt_init(pb, R, t, m);
-      pnp_lm(pb, R, t, 6, m);
+      if (from_scratch) pnp_dlt_init(pb, R, t, &m);
+      pnp_lm(pb, R, t, 6, &m);
     }
     int inl = 0;
     double err = 0.0;
-    pmask_t im = 0;
+    pmask_t im = pm_none();
     for (int i = 0; i < n_pts; ++i) {
-      double xc[3];
-      for (int a = 0; a < 3; ++a) xc[a] = R[a][0] * pb.X[i][0] + R[a][1] * pb.X[i][1] + R[a][2] * pb.X[i][2] + t[a];
-      const double ru = pb.fx * xc[0] / xc[2] + pb.cx - pb.uv[i][0];
-      const double rv = pb.fy * xc[1] / xc[2] + pb.cy - pb.uv[i][1];
+      double xc[3], ru, rv;
+      pnp_point(pb, i, R, t, xc, ru, rv);
       const double e2 = ru * ru + rv * rv;
-      if (e2 <= thr2) { ++inl; im |= 1ull << i; }   // reprojection error only, as cv2's RANSAC callback
+      if (e2 <= thr2) { ++inl; pm_set(im, i); }   // reprojection error only, as cv2's RANSAC callback
       err += fmin(e2, thr2);
     }
     bool ok = isfinite(err);
@@ -1034,7 +1072,7 @@ __global__ void __launch_bounds__(128) pnp_hypothesis_kernel(const float* __rest
     float* P = poses + static_cast<long long>(q) * 16;
     for (int i = 0; i < 16; ++i) P[i] = 0.f;
     if (best_inl >= 0) {
-      if (best_inl >= 4 && best_mask != all_mask) pnp_lm(pb, bestR, bestT, max_iter, best_mask);  // polish on the inliers
+      if (best_inl >= 4 && !pm_equal(best_mask, all_mask)) pnp_lm(pb, bestR, bestT, max_iter, &best_mask);  // polish on the inliers
       bool ok = true;
       for (int a = 0; a < 3; ++a) { ok = ok && isfinite(bestT[a]); for (int b = 0; b < 3; ++b) ok = ok && isfinite(bestR[a][b]); }
       if (ok) {
@@ -1175,8 +1213,8 @@ cudaError_t pose_metrics(const float* pose_pred, const float* pose_gt, const flo
 cudaError_t pnp_solve(const float* corners_px, const float* bbox3d, const float* K, float* poses, const PnpOpts& o, int B,
                       int n_pts, cudaStream_t s, float* rec, const float* corners_norm) {
   if (B <= 0) return cudaSuccess;
-  if (n_pts < 6 || n_pts > PNP_MAXPTS) return cudaErrorInvalidValue;
   if (o.mode != 0 && o.mode != 1) return cudaErrorNotSupported;
+  if (n_pts < 6 || n_pts > (o.mode == 1 ? PNP_MAXPTS_POOLED : PNP_MAXPTS)) return cudaErrorInvalidValue;
   const int max_iter = o.max_iter > 0 ? o.max_iter : 30;  // converged within 15 on realistic corners; OpenCV caps its LM at 20
   if (o.mode == 1) {
     const int n_hyp = o.n_hyp > 0 ? o.n_hyp : 154;

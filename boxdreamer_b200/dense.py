@@ -175,7 +175,7 @@ def process_dense_input(data, pose_feat, frames, camera_mask, rgb_feature, image
     return data, pose_feat, frames, camera_mask, rgb_feature, image_masks
 
 
-MAX_POOLED_POINTS = 64   # PNP_MAXPTS of csrc/post.cu (pooled robust PnP: n_sub sub-batches x 8 corners)
+MAX_POOLED_POINTS = 256   # PNP_MAXPTS_POOLED of csrc/post.cu (pooled robust PnP: n_sub sub-batches x 8 corners)
 
 
 def process_multi_round(data, pose_feat, frames, camera_mask, rgb_feature, image_masks, decoder, dense_cfg, bbox_representation,

@@ -101,7 +101,7 @@ typedef struct {
 } bd_pnp_opts;
 
 /* recover_pose_from_bb8 (utils/box_utils.py:113-199) / recover_pose_from_dense_bb8 (:202-304):
- * corners_px [B,n,2], bbox3d [B,n,3], K [B,3,3] (fp32), 6 <= n <= 64
+ * corners_px [B,n,2], bbox3d [B,n,3], K [B,3,3] (fp32), 6 <= n <= 64 (mode 0) / 256 (mode 1: pooled proposals of up to 32 sub-batches)
  * -> poses [B,4,4] fp32 world->camera (OpenCV convention); a failed solve leaves the zero matrix. */
 int bd_pnp(bd_handle h, const float* corners_px, const float* bbox3d, const float* K, float* poses_out, const bd_pnp_opts* opts,
            int32_t B, int32_t n_pts, void* stream);

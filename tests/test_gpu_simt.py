@@ -195,6 +195,40 @@ def test_pnp_hypothesis_mode_rejects_outlier_corners(lib):
     assert np.median(d) < 0.2  # clean corners: the hypothesis mode may drop a noisy corner but stays at the same solution
 
 
+@pytest.mark.parametrize("n_prop", [8, 16, 32])
+def test_pnp_pooled_points_beyond_64(lib, n_prop):
+    """Robust mode on the pooled proposals of the dense multi-round path with MORE than 8 sub-batches (the reference's
+    recover_pose_from_dense_bb8, box_utils.py:202-304, hands all N*8 pairs to solvePnPRansac): n_prop proposals x 8 corners =
+    64 / 128 / 256 2D-3D pairs per query, 0.5 px noise, a quarter of the proposals displaced as a whole by 15-40 px.  The pose
+    must be recovered (median < 0.3 deg, >= 95 % within 1 deg); the iterative mode keeps rejecting more than 64 pairs."""
+    import ctypes as C
+    from boxdreamer_b200 import synth
+    nq = 64
+    c2, X3, Ks, gt = synth.synth_pnp_cases(nq, 0.0, seed=78)
+    rng = np.random.Generator(np.random.PCG64(11 + n_prop))
+    corners = np.repeat(c2[:, None], n_prop, axis=1) + rng.normal(0, 0.5, size=(nq, n_prop, 8, 2)).astype(np.float32)
+    n_bad = n_prop // 4
+    for i in range(nq):
+        for j in rng.choice(n_prop, size=n_bad, replace=False):
+            corners[i, j] += (rng.uniform(15, 40, size=2) * rng.choice([-1.0, 1.0], size=2)).astype(np.float32)
+    pts2 = torch.from_numpy(corners.reshape(nq, n_prop * 8, 2).astype(np.float32)).cuda().contiguous()
+    pts3 = torch.from_numpy(np.repeat(X3[:, None], n_prop, axis=1).reshape(nq, n_prop * 8, 3).astype(np.float32)).cuda().contiguous()
+    Kc = torch.from_numpy(Ks).cuda()
+    poses = torch.empty(nq, 4, 4, device="cuda")
+    opts = _lib.BdPnpOpts(1, 256, 2.0, 3, 30)
+    _lib.check(lib.bd_pnp(None, _lib.ptr(pts2), _lib.ptr(pts3), _lib.ptr(Kc), _lib.ptr(poses), C.byref(opts), nq, n_prop * 8, sp()))
+    torch.cuda.synchronize()
+    P = poses.cpu().numpy().astype(np.float64)
+    err = np.array([_rot_err_deg(P[i, :3, :3], gt[i, :, :3]) for i in range(nq)])
+    print(f"{n_prop * 8} pooled pairs, {n_bad} displaced proposals: median {np.median(err):.3f} deg, <1deg {np.mean(err < 1):.3f}")
+    assert np.median(err) < 0.3 and np.mean(err < 1.0) >= 0.95
+    if n_prop * 8 > 64:
+        rc = lib.bd_pnp(None, _lib.ptr(pts2), _lib.ptr(pts3), _lib.ptr(Kc), _lib.ptr(poses), None, nq, n_prop * 8, sp())
+        assert rc != 0, "the iterative mode takes at most 64 pairs"
+    rc = lib.bd_pnp(None, _lib.ptr(pts2), _lib.ptr(pts3), _lib.ptr(Kc), _lib.ptr(poses), C.byref(opts), nq, 257, sp())
+    assert rc != 0
+
+
 def test_bbox_heatmap_rasteriser_matches_restatement(lib):
     """bd_make_bbox_features (device) vs synth.make_heatmaps, the torch restatement pinned bit-exact to the dataset's
     make_bbox_features on CPU (tests/test_oracle_vs_reference.py).  Every operation but exp is a correctly rounded fp32

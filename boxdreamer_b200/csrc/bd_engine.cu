@@ -75,6 +75,10 @@ struct bd_engine {
     bool pending = false;          // submitted, not yet waited for
   };
   HostSlot slot[2];
+  // Cross-stream ordering of the ONE workspace: device-pointer entries run on the caller's stream, host-buffer entries on
+  // host_stream / copy_stream.  Each side waits (on the device, cudaStreamWaitEvent) for the other's last recorded work.
+  cudaEvent_t dev_ev = nullptr;      // end of the latest device-pointer entry, recorded on the caller's stream
+  bool dev_ev_valid = false;
   float* pos_dec = nullptr;  // f32 [P, d] 2-D sincos table
   cudaStream_t host_stream = nullptr;
   cudaStream_t copy_stream = nullptr;
@@ -246,6 +250,7 @@ extern "C" int bd_destroy(bd_handle e) {
   }
   drop_graphs(e);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  if (e->dev_ev) cudaEventDestroy(e->dev_ev);
   delete e;
   return BD_OK;
 }
@@ -553,6 +558,20 @@ static int decoder_forward_impl(bd_engine* e, const void* bbox_feat, int dtype, 
   return BD_OK;
 }
 
+// A device-pointer entry on stream `s` starts after every submitted host batch has finished with the workspace ...
+static int order_after_host_batches(bd_engine* e, cudaStream_t s) {
+  for (auto& sl : e->slot)
+    if (sl.done && sl.pending) CK(cudaStreamWaitEvent(s, sl.done, 0));
+  return BD_OK;
+}
+// ... and leaves a marker the next host batch waits for.
+static int mark_device_entry_end(bd_engine* e, cudaStream_t s) {
+  if (!e->dev_ev) CK(cudaEventCreateWithFlags(&e->dev_ev, cudaEventDisableTiming));
+  CK(cudaEventRecord(e->dev_ev, s));
+  e->dev_ev_valid = true;
+  return BD_OK;
+}
+
 // ---- CUDA graphs of the launch chain --------------------------------------------------------------------------------------
 // A forward is ~220 launches, each with host-side work (tensor-map encoding, weight look-ups): at batch 1 the host, not the GPU,
 // sets the latency.  `body(stream)` enqueues a stage that reads and writes engine-owned buffers only, so its launches can be
@@ -629,15 +648,20 @@ static std::vector<long long> graph_key(int stage, int slot, int dtype, int a, i
 extern "C" int bd_dino_forward(bd_handle e, const void* images, int32_t dtype, float* feats_out, int32_t L, void* stream) {
   if (!e || !images || !feats_out) return fail(BD_ERR_INVALID, "bd_dino_forward: null argument");
   DevGuard dev_guard(e);
-  return dino_forward_impl(e, images, dtype, feats_out, L, reinterpret_cast<cudaStream_t>(stream));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int r = order_after_host_batches(e, s);
+  if (r == BD_OK) r = dino_forward_impl(e, images, dtype, feats_out, L, s);
+  return r != BD_OK ? r : mark_device_entry_end(e, s);
 }
 
 extern "C" int bd_decoder_forward(bd_handle e, const void* bbox_feat, int32_t dtype, const float* feats, const int64_t* query_idx,
                                   float* heat_out, float* logits_out, int32_t B, int32_t T, void* stream) {
   if (!e || !bbox_feat || !feats || !query_idx || !heat_out) return fail(BD_ERR_INVALID, "bd_decoder_forward: null argument");
   DevGuard dev_guard(e);
-  return decoder_forward_impl(e, bbox_feat, dtype, feats, false, query_idx, heat_out, logits_out, B, T,
-                              reinterpret_cast<cudaStream_t>(stream));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int r = order_after_host_batches(e, s);
+  if (r == BD_OK) r = decoder_forward_impl(e, bbox_feat, dtype, feats, false, query_idx, heat_out, logits_out, B, T, s);
+  return r != BD_OK ? r : mark_device_entry_end(e, s);
 }
 
 extern "C" int bd_corners_topk(bd_handle e, const float* heat, float* corners_px, float* corners_norm, int32_t* idx_out, int32_t B,
@@ -662,12 +686,24 @@ extern "C" int bd_pnp(bd_handle e, const float* corners_px, const float* bbox3d,
 
 // bd_forward / bd_forward_packed: device pointers in, device results out.  Null result pointers select the engine's own buffers;
 // rec_out (mode 0 only) receives the packed [B, 28] record written by the PnP kernel's epilogue.
+static int forward_device_inner(bd_handle e, const void* images, const void* bbox_feat, int32_t in_dtype, const int64_t* query_idx,
+                                const float* bbox3d_q, const float* K_q, float* heat_out, float* corners_px, float* corners_norm,
+                                float* poses_out, float* rec_out, const bd_pnp_opts* opts, int32_t B, int32_t T, cudaStream_t s);
 static int forward_device_impl(bd_handle e, const void* images, const void* bbox_feat, int32_t in_dtype, const int64_t* query_idx,
                                const float* bbox3d_q, const float* K_q, float* heat_out, float* corners_px, float* corners_norm,
                                float* poses_out, float* rec_out, const bd_pnp_opts* opts, int32_t B, int32_t T, void* stream) {
   DevGuard dev_guard(e);
   if (B <= 0 || T <= 0 || B > e->Bmax || T > e->Tmax) return fail(BD_ERR_INVALID, "bd_forward: B/T exceed the workspace");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int r = order_after_host_batches(e, s);
+  if (r == BD_OK)
+    r = forward_device_inner(e, images, bbox_feat, in_dtype, query_idx, bbox3d_q, K_q, heat_out, corners_px, corners_norm, poses_out, rec_out,
+                             opts, B, T, s);
+  return r != BD_OK ? r : mark_device_entry_end(e, s);
+}
+static int forward_device_inner(bd_handle e, const void* images, const void* bbox_feat, int32_t in_dtype, const int64_t* query_idx,
+                                const float* bbox3d_q, const float* K_q, float* heat_out, float* corners_px, float* corners_norm,
+                                float* poses_out, float* rec_out, const bd_pnp_opts* opts, int32_t B, int32_t T, cudaStream_t s) {
   const PnpOpts po = to_opts(opts);
   if (po.mode != 0 && po.mode != 1) return fail(BD_ERR_UNSUPPORTED, "bd_forward: pnp mode not built");
   if (rec_out && po.mode != 0) return fail(BD_ERR_UNSUPPORTED, "bd_forward_packed: the packed record is written by the iterative PnP kernel (mode 0) only");
@@ -676,9 +712,6 @@ static int forward_device_impl(bd_handle e, const void* images, const void* bbox
     // the captured launch chain; the results are copied out of the workspace afterwards
     int r = ensure_staging(e, 0);
     if (r != BD_OK) return r;
-    if (e->slot[0].pending) {   // a submitted host batch still owns slot 0: let it finish before its staging is overwritten
-      CK(cudaEventSynchronize(e->slot[0].done));
-    }
     const size_t es = in_dtype == BD_BF16 ? 2 : 4, SS = static_cast<size_t>(e->S) * e->S, L = static_cast<size_t>(B) * T;
     CK(cudaMemcpyAsync(e->slot[0].in_images, images, L * 3 * SS * es, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(e->slot[0].in_bbox, bbox_feat, L * 8 * SS * es, cudaMemcpyDeviceToDevice, s));
@@ -767,6 +800,10 @@ static int host_submit_impl(bd_handle e, int k, const void* images_host, const v
     CK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
   }
   cudaStream_t s = e->host_stream;
+  if (e->dev_ev_valid) {   // a device-pointer entry may still be using the workspace (and slot 0's staging) on the caller's stream
+    CK(cudaStreamWaitEvent(s, e->dev_ev, 0));
+    CK(cudaStreamWaitEvent(e->copy_stream, e->dev_ev, 0));
+  }
   // Copy order = consumption order: the encoder only needs the images, so they go first; the reference heat maps (73 % of
   // the bytes) follow and land while the encoder runs.  The decoder, the corner extraction and PnP then see the whole batch
   // once.  The images can be split into `nchunk` pieces of whole queries (first one half-sized) so that the encoder starts

@@ -389,3 +389,36 @@ def test_last_decoder_block_on_query_rows_336px(monkeypatch):
         torch.cuda.synchronize()
         outs.append(logits.clone())
     assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
+
+
+def test_mixed_host_and_device_entries_share_the_workspace_safely(weights):
+    """A host batch in flight (bd_forward_host_submit, internal streams) and device-pointer calls on the caller's stream use the
+    same workspace: each side must wait for the other on the device.  Interleave them without any host synchronisation in
+    between and compare every result with the same call made alone."""
+    m = _model(weights, "bf16")
+    B, T = 2, 3
+    def make(seed):
+        data = synth.synth_inputs(B, T, 224, seed=seed, dtype=torch.bfloat16)
+        mask = torch.zeros(B, T, dtype=torch.bool)
+        mask[torch.arange(B), data["query_idx"]] = True
+        return (data["images"].contiguous(), data["bbox_feat"].contiguous(), data["query_idx"].contiguous(),
+                data["bbox_3d"][mask].float().contiguous(), data["non_ndc_intrinsics"][mask].float().contiguous())
+    host = [tuple(t.pin_memory() for t in make(401 + i)) for i in range(3)]
+    dev = [tuple(t.cuda() for t in make(501 + i)) for i in range(3)]
+    eng = m._engine_for(dev[0][0], B, T)
+    ref_h = [[t.clone() for t in eng.forward_host(*h, want_heat=True)] for h in host]
+    ref_d = [[t.clone() for t in eng.forward(*d)] for d in dev]
+    torch.cuda.synchronize()
+    for rnd in range(2):
+        got_h, got_d = [], []
+        for i in range(3):
+            got_h.append(eng.forward_host_submit(i & 1, *host[i], want_heat=True))
+            got_d.append(eng.forward(*dev[i]))          # no synchronisation: ordered on the device
+            if i > 0:
+                eng.forward_host_wait((i - 1) & 1)
+        eng.forward_host_wait(0)
+        eng.forward_host_wait(1)
+        torch.cuda.synchronize()
+        for i in range(3):
+            assert all(torch.equal(g, r) for g, r in zip(got_h[i], ref_h[i])), f"round {rnd}: host batch {i} corrupted by a device call"
+            assert all(torch.equal(g, r) for g, r in zip(got_d[i], ref_d[i])), f"round {rnd}: device call {i} corrupted by a host batch"

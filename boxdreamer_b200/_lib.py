@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("BD_LIB_PATH") or os.path.join(HERE, "libboxdreamer_b2
 BD_F32, BD_BF16 = 0, 1
 PRECISION_EXACT, PRECISION_BF16 = 0, 1
 EPI_F32, EPI_GELU, EPI_RESID, EPI_QKV, EPI_ACT = 0, 1, 2, 3, 4
-PROF_CATS = ["gemm_qkv", "attention", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_other", "layernorm", "glue", "topk", "pnp", "attention_dino"]
+PROF_CATS = ["gemm_qkv", "attention", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_other", "layernorm", "glue", "topk", "pnp", "attention_dino", "attention_window"]
 
 # every symbol include/boxdreamer_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [

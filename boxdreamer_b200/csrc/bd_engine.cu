@@ -450,7 +450,7 @@ static int run_block_query_rows(bd_engine* e, float* X, const std::string& p, in
   q.k_norm_w = WF(e, p + "attn.k_norm.weight");
   q.seq = seq; q.seq_pad = seq_pad; q.heads = heads; q.head_dim = hd; q.rms_eps = 1e-6f;
   LAUNCH(BD_PROF_GEMM_QKV, 1, linear(e, e->H, p + "attn.qkv.weight", M, 3 * d, d, EPI_QKV, q, s));
-  LAUNCH(BD_PROF_ATTENTION, 1,
+  LAUNCH(BD_PROF_ATTENTION_WINDOW, 1,
          attention_tc_window(reinterpret_cast<const bf16*>(e->Q), reinterpret_cast<const bf16*>(e->K), reinterpret_cast<const bf16*>(e->V),
                              reinterpret_cast<bf16*>(e->O), B, heads, hd, seq, seq_pad, 1.0f / sqrtf(static_cast<float>(hd)),
                              reinterpret_cast<const long long*>(query_idx), P, s));

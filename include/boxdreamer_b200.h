@@ -194,7 +194,7 @@ int bd_layernorm(const float* x, const float* w, const float* b, float eps, floa
 enum {
   BD_PROF_GEMM_QKV = 0, BD_PROF_ATTENTION = 1 /* decoder (BETR) attention */, BD_PROF_GEMM_PROJ = 2, BD_PROF_GEMM_FC1 = 3, BD_PROF_GEMM_FC2 = 4,
   BD_PROF_GEMM_OTHER = 5, BD_PROF_LAYERNORM = 6, BD_PROF_GLUE = 7, BD_PROF_TOPK = 8, BD_PROF_PNP = 9,
-  BD_PROF_ATTENTION_DINO = 10, BD_PROF_NCAT = 11
+  BD_PROF_ATTENTION_DINO = 10, BD_PROF_ATTENTION_WINDOW = 11 /* the decoder's last block: query-window launch */, BD_PROF_NCAT = 12
 };
 /* kernels this handle has launched so far */
 long long bd_launch_count(bd_handle h);

@@ -422,3 +422,83 @@ def test_mixed_host_and_device_entries_share_the_workspace_safely(weights):
         for i in range(3):
             assert all(torch.equal(g, r) for g, r in zip(got_h[i], ref_h[i])), f"round {rnd}: host batch {i} corrupted by a device call"
             assert all(torch.equal(g, r) for g, r in zip(got_d[i], ref_d[i])), f"round {rnd}: device call {i} corrupted by a host batch"
+
+
+def test_full_config2_size_properties(weights, monkeypatch):
+    """BASELINE config 2 at its full size (64 queries x 6 views, 224 px, bf16) -- too large for the CPU oracle, so checked through
+    size-independent properties of the path: (a) determinism (two runs bit-identical), (b) every query is independent: permuting
+    the batch permutes the results bit for bit (no cross-sample operation), and a query evaluated alone (B = 1, graph
+    replay path) equals its row of the batch, (c) the query-window last block equals the full one at this size, (d) poses are
+    rigid (R orthonormal, det +1) or the zero matrix of a failed solve."""
+    B, T = 64, 6
+    data = synth.synth_inputs(B, T, 224, seed=4242, dtype=torch.bfloat16)
+    mask = torch.zeros(B, T, dtype=torch.bool)
+    mask[torch.arange(B), data["query_idx"]] = True
+    img, bb, qi = data["images"].cuda().contiguous(), data["bbox_feat"].cuda().contiguous(), data["query_idx"].cuda()
+    X = data["bbox_3d"][mask].float().cuda().contiguous()
+    K = data["non_ndc_intrinsics"][mask].float().cuda().contiguous()
+    m = _model(weights, "bf16")
+    eng = m._engine_for(img, B, T)
+    a = [t.clone() for t in eng.forward(img, bb, qi, X, K)]
+    b = eng.forward(img, bb, qi, X, K)
+    torch.cuda.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(a, b)), "not deterministic"
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(5)).cuda()
+    p = eng.forward(img[perm].contiguous(), bb[perm].contiguous(), qi[perm].contiguous(), X[perm].contiguous(), K[perm].contiguous())
+    torch.cuda.synchronize()
+    for x, y, nm in zip(a, p, ("heat", "corners_px", "corners_norm", "poses")):
+        assert torch.equal(x[perm], y), f"{nm}: batch permutation is not a permutation of the results"
+    for i in (0, 37):
+        one = eng.forward(img[i:i + 1].contiguous(), bb[i:i + 1].contiguous(), qi[i:i + 1].contiguous(), X[i:i + 1].contiguous(),
+                          K[i:i + 1].contiguous())
+        one = eng.forward(img[i:i + 1].contiguous(), bb[i:i + 1].contiguous(), qi[i:i + 1].contiguous(), X[i:i + 1].contiguous(),
+                          K[i:i + 1].contiguous())   # second call: captured graph
+        torch.cuda.synchronize()
+        assert torch.equal(one[1][0], a[1][i]) and torch.equal(one[3][0], a[3][i]), f"query {i} alone differs from its batch row"
+    feats = eng.dino_forward(img.view(B * T, 3, 224, 224))
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("BD_LAST_LAYER_PRUNE", flag)
+        outs.append(eng.decoder_forward(bb, feats, qi, want_logits=True)[1].clone())
+    assert torch.equal(outs[0], outs[1]), "query-window last block differs from the full block at B = 64"
+    R = a[3][:, :3, :3].double()
+    ok = a[3][:, 3, 3] == 1
+    assert ok.any()
+    eye = torch.eye(3, dtype=torch.float64, device=R.device)
+    assert float((R[ok] @ R[ok].transpose(1, 2) - eye).abs().max()) < 1e-5 and float((torch.linalg.det(R[ok]) - 1).abs().max()) < 1e-5
+    assert float(a[3][~ok].abs().max()) == 0.0 if (~ok).any() else True
+
+
+def test_config4_shape_properties(monkeypatch):
+    """BASELINE config 4's shape (16 references, 336 px: N = 17 * 576 = 9792 decoder tokens per query) on a small batch: the
+    long-sequence path of the attention kernel (102 key tiles, trimmed tail), checked through the same size-independent properties
+    -- determinism, a query alone equals its batch row, query-window last block == full block."""
+    dec, dino = synth.synth_decoder_state_dict(0), synth.synth_dino_state_dict(0)
+    m = BoxDreamer(_config(336), precision="bf16")
+    m.load_state_dict(dec, strict=True)
+    m.rgb_encoder.model.load_state_dict(dino, strict=True)
+    m = m.cuda().eval()
+    B, T = 3, 17
+    data = synth.synth_inputs(B, T, 336, seed=4343, dtype=torch.bfloat16)
+    data["query_idx"] = torch.tensor([16, 0, 9], dtype=torch.int64)
+    mask = torch.zeros(B, T, dtype=torch.bool)
+    mask[torch.arange(B), data["query_idx"]] = True
+    img, bb, qi = data["images"].cuda().contiguous(), data["bbox_feat"].cuda().contiguous(), data["query_idx"].cuda()
+    X = data["bbox_3d"][mask].float().cuda().contiguous()
+    K = data["non_ndc_intrinsics"][mask].float().cuda().contiguous()
+    eng = m._engine_for(img, B, T)
+    a = [t.clone() for t in eng.forward(img, bb, qi, X, K)]
+    b = eng.forward(img, bb, qi, X, K)
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(x).all() for x in a) and all(torch.equal(x, y) for x, y in zip(a, b))
+    for i in range(B):
+        one = eng.forward(img[i:i + 1].contiguous(), bb[i:i + 1].contiguous(), qi[i:i + 1].contiguous(), X[i:i + 1].contiguous(),
+                          K[i:i + 1].contiguous())
+        torch.cuda.synchronize()
+        assert torch.equal(one[0][0], a[0][i]) and torch.equal(one[3][0], a[3][i]), f"query {i} alone differs from its batch row"
+    feats = eng.dino_forward(img.view(B * T, 3, 336, 336))
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("BD_LAST_LAYER_PRUNE", flag)
+        outs.append(eng.decoder_forward(bb, feats, qi, want_logits=True)[1].clone())
+    assert torch.equal(outs[0], outs[1])

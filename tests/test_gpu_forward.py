@@ -502,3 +502,24 @@ def test_config4_shape_properties(monkeypatch):
         monkeypatch.setenv("BD_LAST_LAYER_PRUNE", flag)
         outs.append(eng.decoder_forward(bb, feats, qi, want_logits=True)[1].clone())
     assert torch.equal(outs[0], outs[1])
+
+
+def test_query_without_references_matches_oracle(weights):
+    """Edge case T = 1 (a query view and no reference view): the decoder sequence is the query's P tokens alone.  Exact path
+    against the oracle at the 1e-4 gate, bf16 path at its statistical gate; corners bit-exact on the exact path."""
+    from oracle import boxdreamer_oracle as O
+    dec, dino = weights
+    B, T = 2, 1
+    data = synth.synth_inputs(B, T, 224, seed=93)
+    with torch.no_grad():
+        ref = O.forward(data, dec, dino, with_pnp=False)
+    for precision, dtype, tol in (("exact", torch.float32, 1e-4), ("bf16", torch.bfloat16, 1.5e-2)):
+        m = _model(weights, precision)
+        d = _to_cuda({k: (v.to(dtype) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in data.items()})
+        eng = m._engine_for(d["images"], B, T)
+        feats = eng.dino_forward(d["images"].view(B * T, 3, 224, 224).contiguous())
+        heat, logits = eng.decoder_forward(d["bbox_feat"].contiguous(), feats, d["query_idx"], want_logits=True)
+        assert _scaled(logits.view(B, 256, 1568), ref["logits"]) <= tol, precision
+        if precision == "exact":
+            px, nm = eng.corners_topk(heat)
+            assert torch.allclose(px.cpu(), ref["keypoints_px"], atol=1e-6, rtol=0)

@@ -196,31 +196,38 @@ class Engine:
                                               _lib.stream_ptr()), "bd_forward_packed")
         return rec
 
+    def _pinned_results(self, tag, B, want_heat):
+        """Pinned result buffers (heat | None, corners_px, corners_norm, poses), allocated once per (tag, B) and reused: pinning /
+        unpinning host memory inside the loop synchronises the device and would undo the pipelining of the host entries."""
+        cache = self.__dict__.setdefault("_pinned_cache", {})
+        key = (tag, B)
+        if key not in cache:
+            cache[key] = [None, torch.empty(B, 8, 2, dtype=torch.float32).pin_memory(),
+                          torch.empty(B, 8, 2, dtype=torch.float32).pin_memory(), torch.empty(B, 4, 4, dtype=torch.float32).pin_memory()]
+        bufs = cache[key]
+        if want_heat and bufs[0] is None:
+            bufs[0] = torch.empty(B, 8, self.S, self.S, dtype=torch.float32).pin_memory()
+        return (bufs[0] if want_heat else None), bufs[1], bufs[2], bufs[3]
+
     @_on_device
     def forward_host(self, images, bbox_feat, query_idx, bbox3d_q, K_q, want_heat=False, opts=None):
         """Host tensors in, host tensors out (H2D/D2H inside the call)."""
         B, T = images.shape[:2]
-        heat = torch.empty(B, 8, self.S, self.S, dtype=torch.float32).pin_memory() if want_heat else None
-        px = torch.empty(B, 8, 2, dtype=torch.float32).pin_memory()
-        nm = torch.empty(B, 8, 2, dtype=torch.float32).pin_memory()
-        poses = torch.empty(B, 4, 4, dtype=torch.float32).pin_memory()
+        heat, px, nm, poses = self._pinned_results("sync", B, want_heat)
         o = C.byref(opts) if opts is not None else None
         _lib.check(self.lib.bd_forward_host(self.handle, _lib.ptr(images), _lib.ptr(bbox_feat), self._dt(images),
                                             _lib.ptr(query_idx), _lib.ptr(bbox3d_q), _lib.ptr(K_q), _lib.ptr(heat),
                                             _lib.ptr(px), _lib.ptr(nm), _lib.ptr(poses), o, B, T), "bd_forward_host")
-        return heat, px, nm, poses
-
+        return (heat.clone() if heat is not None else None), px.clone(), nm.clone(), poses.clone()
 
     @_on_device
     def forward_host_submit(self, slot, images, bbox_feat, query_idx, bbox3d_q, K_q, bbox_px=None, want_heat=False, opts=None):
         """Pipelined host entry: enqueue one batch on staging slot 0 / 1 and return the (pinned) result tensors, which are
-        filled once `forward_host_wait(slot)` returns.  Pass `bbox_px` [B,T,8,2] instead of `bbox_feat` (None) to have the
-        reference heat maps rasterised on the device.  The input tensors must stay alive until the wait."""
+        filled once `forward_host_wait(slot)` returns and stay valid until the same slot is submitted again (they are reused).
+        Pass `bbox_px` [B,T,8,2] instead of `bbox_feat` (None) to have the reference heat maps rasterised on the device.  The
+        input tensors must stay alive until the wait."""
         B, T = images.shape[:2]
-        heat = torch.empty(B, 8, self.S, self.S, dtype=torch.float32).pin_memory() if want_heat else None
-        px = torch.empty(B, 8, 2, dtype=torch.float32).pin_memory()
-        nm = torch.empty(B, 8, 2, dtype=torch.float32).pin_memory()
-        poses = torch.empty(B, 4, 4, dtype=torch.float32).pin_memory()
+        heat, px, nm, poses = self._pinned_results(("slot", slot), B, want_heat)
         o = C.byref(opts) if opts is not None else None
         _lib.check(self.lib.bd_forward_host_submit(self.handle, slot, _lib.ptr(images), _lib.ptr(bbox_feat), _lib.ptr(bbox_px),
                                                    self._dt(images), _lib.ptr(query_idx), _lib.ptr(bbox3d_q), _lib.ptr(K_q),
@@ -239,15 +246,12 @@ class Engine:
     def forward_host_px(self, images, bbox_px, query_idx, bbox3d_q, K_q, want_heat=False, opts=None):
         """forward_host with the reference heat maps rasterised on the device from bbox_px [B,T,8,2] (host, fp32)."""
         B, T = images.shape[:2]
-        heat = torch.empty(B, 8, self.S, self.S, dtype=torch.float32).pin_memory() if want_heat else None
-        px = torch.empty(B, 8, 2, dtype=torch.float32).pin_memory()
-        nm = torch.empty(B, 8, 2, dtype=torch.float32).pin_memory()
-        poses = torch.empty(B, 4, 4, dtype=torch.float32).pin_memory()
+        heat, px, nm, poses = self._pinned_results("sync", B, want_heat)
         o = C.byref(opts) if opts is not None else None
         _lib.check(self.lib.bd_forward_host_px(self.handle, _lib.ptr(images), _lib.ptr(bbox_px), self._dt(images),
                                                _lib.ptr(query_idx), _lib.ptr(bbox3d_q), _lib.ptr(K_q), _lib.ptr(heat),
                                                _lib.ptr(px), _lib.ptr(nm), _lib.ptr(poses), o, B, T), "bd_forward_host_px")
-        return heat, px, nm, poses
+        return (heat.clone() if heat is not None else None), px.clone(), nm.clone(), poses.clone()
 
 
 # ----------------------------------------------------------------------------------------------

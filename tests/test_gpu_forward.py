@@ -416,8 +416,10 @@ def test_mixed_host_and_device_entries_share_the_workspace_safely(weights):
             got_d.append(eng.forward(*dev[i]))          # no synchronisation: ordered on the device
             if i > 0:
                 eng.forward_host_wait((i - 1) & 1)
+                got_h[i - 1] = [t.clone() for t in got_h[i - 1]]   # a slot's pinned result buffers are reused by its next submit
         eng.forward_host_wait(0)
         eng.forward_host_wait(1)
+        got_h[2] = [t.clone() for t in got_h[2]]
         torch.cuda.synchronize()
         for i in range(3):
             assert all(torch.equal(g, r) for g, r in zip(got_h[i], ref_h[i])), f"round {rnd}: host batch {i} corrupted by a device call"

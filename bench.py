@@ -465,34 +465,6 @@ def run_ours(args, rank, world, local_rank):
     ms = float(t.item())
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- the same loop with the decoder's last block computed for ALL rows, as the reference does (the default engine restricts it
-    # to the query view's rows, the only ones the head reads: bit-identical results, 3 % fewer FLOPs) -- reported beside `value` ----
-    value_full_last_block = None
-    if not args.quick:
-        def timed_loop():
-            for _ in range(2):
-                step()
-            drain()
-            barrier()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for _ in range(args.steps):
-                step()
-            drain()
-            f1.record()
-            barrier()
-            tf = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-            return world * B * args.steps / (float(tf.item()) / 1e3)
-        os.environ["BD_LAST_LAYER_PRUNE"] = "0"
-        try:
-            v_full = timed_loop()
-        finally:
-            del os.environ["BD_LAST_LAYER_PRUNE"]
-        # measured back to back on the warmed-up, power-capped GPU: full block first, then the default engine again
-        value_full_last_block = {"full_last_block": v_full, "query_rows_only_measured_right_after": timed_loop(), "unit": UNIT}
-
     # ---- in-step per-kernel timing (CUDA events on the launching stream, same workload) ----
     import ctypes as C
     _lib.check(lib.bd_profile_enable(eng.handle, 1))
@@ -659,6 +631,34 @@ def run_ours(args, rank, world, local_rank):
                               "(BoxDreamerModel.py:341-344, 308 MB at B=64 bf16); lazy = model.write_pred_bbox=False returns the query heat maps "
                               "as data['pred_bbox_query'] [B,8,S,S] only"}
         del dd
+
+    # ---- the same loop with the decoder's last block computed for ALL rows, as the reference does (the default engine restricts it
+    # to the query view's rows, the only ones the head reads: bit-identical results, 3 % fewer FLOPs) -- reported beside `value` ----
+    value_full_last_block = None
+    if not args.quick:
+        def timed_loop():
+            for _ in range(2):
+                step()
+            drain()
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(args.steps):
+                step()
+            drain()
+            f1.record()
+            barrier()
+            tf = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            return world * B * args.steps / (float(tf.item()) / 1e3)
+        os.environ["BD_LAST_LAYER_PRUNE"] = "0"
+        try:
+            v_full = timed_loop()
+        finally:
+            del os.environ["BD_LAST_LAYER_PRUNE"]
+        # measured back to back on the warmed-up, power-capped GPU: full block first, then the default engine again
+        value_full_last_block = {"full_last_block": v_full, "query_rows_only_measured_right_after": timed_loop(), "unit": UNIT}
 
     cpu_base, parity, ref_gpu = None, None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:

@@ -525,3 +525,29 @@ def test_query_without_references_matches_oracle(weights):
         if precision == "exact":
             px, nm = eng.corners_topk(heat)
             assert torch.allclose(px.cpu(), ref["keypoints_px"], atol=1e-6, rtol=0)
+
+
+def test_new_entries_validate_their_arguments(weights):
+    """bd_forward_packed / bd_forward_host_submit / _wait fail loudly (status + bd_last_error) instead of guessing: robust PnP mode
+    with a packed record, staging slots other than 0 / 1, null result pointers; waiting on an idle slot is a no-op."""
+    import ctypes as C
+    m = _model(weights, "bf16")
+    B, T = 1, 2
+    data = synth.synth_inputs(B, T, 224, seed=95, dtype=torch.bfloat16)
+    mask = torch.zeros(B, T, dtype=torch.bool)
+    mask[torch.arange(B), data["query_idx"]] = True
+    img, bb, qi = data["images"].cuda().contiguous(), data["bbox_feat"].cuda().contiguous(), data["query_idx"].cuda()
+    X = data["bbox_3d"][mask].float().cuda().contiguous()
+    K = data["non_ndc_intrinsics"][mask].float().cuda().contiguous()
+    eng = m._engine_for(img, B, T)
+    with pytest.raises(_lib.BoxDreamerLibError, match="mode 0"):
+        eng.forward_packed(img, bb, qi, X, K, opts=_lib.BdPnpOpts(1, 64, 2.0, 0, 30))
+    host = (img.cpu().pin_memory(), bb.cpu().pin_memory(), qi.cpu(), X.cpu(), K.cpu())
+    with pytest.raises(_lib.BoxDreamerLibError, match="slot"):
+        eng.forward_host_submit(2, *host)
+    assert eng.lib.bd_forward_host_wait(eng.handle, 1) == 0          # nothing submitted on slot 1: returns at once
+    assert eng.lib.bd_forward_host_wait(eng.handle, 5) != 0
+    rc = eng.lib.bd_forward_packed(eng.handle, _lib.ptr(img), _lib.ptr(bb), 1, _lib.ptr(qi), _lib.ptr(X), _lib.ptr(K), None, None, B, T, None)
+    assert rc != 0 and b"null" in eng.lib.bd_last_error()
+    rec = eng.forward_packed(img, bb, qi, X, K)                       # and the valid call still works afterwards
+    assert rec.shape == (B, 28) and torch.isfinite(rec).all()

@@ -115,3 +115,22 @@ def test_matches_reference_functions():
         for key in d2:
             if torch.is_tensor(d2[key]):
                 assert torch.equal(d1[key], d2[key]), key
+
+
+def test_multi_round_rejects_more_pooled_points_than_bd_pnp_takes_before_any_work():
+    """the pooled robust PnP takes n_sub * 8 <= 256 2D-3D pairs (32 sub-batches); a larger reference set must fail with a
+    clear message BEFORE the coarse decoder round runs, not with BD_ERR_INVALID after it.  Sub-batches up to the limit pass the
+    check (here the decoder stub then stops the run)."""
+    class Ran(Exception):
+        pass
+
+    def decoder(*a, **k):
+        raise Ran()
+
+    cfg = {"sub_batch_size": 1, "fine_level": True, "fine_topk": 2, "dense_mem_friendly": False}
+    data, pose_feat, frames, mask, rgb, img_masks = _case(B=1, T=34, S=14, L=4, D=4)        # 33 references -> 33 sub-batches -> 264 pairs
+    with pytest.raises(ValueError, match="264 2D-3D pairs"):
+        dense.process_multi_round(data, pose_feat, frames, mask, rgb, img_masks, decoder, cfg, "heatmap", lambda *a: None)
+    data, pose_feat, frames, mask, rgb, img_masks = _case(B=1, T=33, S=14, L=4, D=4)        # 32 sub-batches -> 256 pairs: accepted
+    with pytest.raises(Ran):
+        dense.process_multi_round(data, pose_feat, frames, mask, rgb, img_masks, decoder, cfg, "heatmap", lambda *a: None)
